@@ -1,0 +1,406 @@
+"""Flat CPU restatements of the reference planners -- TEST INFRASTRUCTURE.
+
+Each function restates one reference algorithm over struct-of-arrays lists
+(node id = creation order) instead of the reference's Node object graph, and
+is pinned against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py -> tests/golden/*.json, tests/test_oracle.py).
+
+Envs are driven exactly like the reference drives them: deep copy + step.
+"""
+import copy
+import math
+
+import numpy as np
+
+
+def _available_actions(state):
+    # deterministic.py:32-35, olop.py:168-171, mcts.py:69-72
+    try:
+        return list(state.get_available_actions())
+    except AttributeError:
+        return list(range(state.action_space.n))
+
+
+class Tree(object):
+    """SoA tree dump shared by the oracle and the CUDA parity tests."""
+
+    def __init__(self):
+        self.parent = []
+        self.action = []
+        self.depth = []
+        self.count = []
+        self.first_child = []
+        self.n_children = []
+
+    def children(self, i):
+        return range(self.first_child[i], self.first_child[i] + self.n_children[i])
+
+    def __len__(self):
+        return len(self.parent)
+
+
+# --------------------------------------------------------------------------
+# OPD -- rl_agents/agents/tree_search/deterministic.py
+# --------------------------------------------------------------------------
+def opd_plan(env, budget, gamma, terminal_reward=0.0, np_random=None):
+    """OptimisticDeterministicPlanner.plan (deterministic.py:116-122) after a
+    reset (deterministic.py:102-104).  Returns (plan, tree)."""
+    t = Tree()
+    t.reward, t.lower, t.upper, t.done = [], [], [], []
+    states = []
+
+    def new_node(parent, action, depth, state):
+        # DeterministicNode.__init__ (deterministic.py:10-19): count = 1
+        t.parent.append(parent)
+        t.action.append(action)
+        t.depth.append(depth)
+        t.count.append(1)
+        t.first_child.append(-1)
+        t.n_children.append(0)
+        t.reward.append(0.0)
+        t.lower.append(0.0)
+        t.upper.append(0.0)
+        t.done.append(False)
+        states.append(state)
+        return len(t.parent) - 1
+
+    root = new_node(-1, -1, 0, env)
+    leaves = [root]
+    terminal_expansions = 0
+    for _ in range(int(budget) // env.action_space.n):          # :118
+        # run(): first arg-max of value_upper over the leaves list (:110)
+        best = leaves[0]
+        for i in leaves[1:]:
+            if t.upper[i] > t.upper[best]:
+                best = i
+        if t.done[best]:
+            terminal_expansions += 1                            # :111-112 (warning)
+        # expand() (:28-43)
+        leaves.remove(best)
+        actions = _available_actions(states[best])
+        t.first_child[best] = len(t.parent)
+        t.n_children[best] = len(actions)
+        d = t.depth[best] + 1
+        for a in actions:
+            c = new_node(best, a, d, copy.deepcopy(states[best]))
+            _, reward, done, _, _ = states[c].step(a)
+            leaves.append(c)
+            # update() (:45-65)
+            if not (0 <= reward <= 1):
+                raise ValueError("This planner assumes that all rewards are normalized in [0, 1]")
+            t.reward[c] = reward
+            t.done[c] = bool(done)
+            t.lower[c] = t.lower[best] + (gamma ** (d - 1)) * reward
+            t.upper[c] = t.lower[c] + (gamma ** d) / (1 - gamma)
+            if done:
+                t.lower[c] = t.upper[c] = t.lower[c] + terminal_reward * (gamma ** d) / (1 - gamma)
+            n = c
+            while n >= 0:                                       # sequence(): self..root
+                t.count[n] += 1
+                n = t.parent[n]
+        states[best] = None
+        # backup_to_root() (:74-79)
+        n = best
+        while n >= 0:
+            t.lower[n] = max(t.lower[c] for c in t.children(n))
+            t.upper[n] = max(t.upper[c] for c in t.children(n))
+            n = t.parent[n]
+    t.terminal_expansions = terminal_expansions
+    t.n_leaves = len(leaves)
+    return greedy_plan(t, t.lower, np_random), t
+
+
+def greedy_plan(t, values, np_random):
+    """AbstractPlanner.get_plan (abstract.py:143-156) with
+    DeterministicNode.selection_rule (deterministic.py:21-26): arg-max of the
+    children values, uniform tie-break through the planner RNG
+    (abstract.py:296-311)."""
+    plan = []
+    node = 0
+    while t.n_children[node] > 0:
+        kids = list(t.children(node))
+        x = np.array([values[c] for c in kids])
+        indices = np.nonzero(x == np.amax(x))[0]
+        index = np_random.choice(indices)
+        plan.append(t.action[kids[index]])
+        node = kids[index]
+    return plan
+
+
+# --------------------------------------------------------------------------
+# MCTS -- rl_agents/agents/tree_search/mcts.py (open loop, K = 1)
+# --------------------------------------------------------------------------
+def olop_horizon(episodes, gamma):
+    # olop.py:42-44
+    return max(int(np.ceil(np.log(episodes) / (2 * np.log(1 / gamma)))), 1)
+
+
+def olop_allocation(budget, gamma):
+    # olop.py:50-62
+    for episodes in range(1, int(budget)):
+        if episodes * olop_horizon(episodes, gamma) > budget:
+            episodes = max(episodes - 1, 1)
+            horizon = olop_horizon(episodes, gamma)
+            break
+    else:
+        raise ValueError("Could not split budget {} with gamma {}".format(budget, gamma))
+    return episodes, horizon
+
+
+def _policy(policy_config, state):
+    """MCTSAgent.policy_factory policies (mcts.py:34-97) -> (actions, probs)."""
+    kind = policy_config["type"]
+    if kind == "random":
+        actions = np.arange(state.action_space.n)
+        return actions, np.ones(len(actions)) / len(actions)
+    if hasattr(state, "get_available_actions"):
+        available = state.get_available_actions()
+    else:
+        available = np.arange(state.action_space.n)
+    uniform = np.ones(len(available)) / len(available)
+    if kind == "random_available":
+        return available, uniform
+    if kind == "preference":
+        for i in range(len(available)):
+            if available[i] == policy_config["action"]:
+                ratio = policy_config.get("ratio", 2)
+                p = np.ones(len(available)) / (len(available) - 1 + ratio)
+                p[i] *= ratio
+                return available, p
+        return available, uniform
+    raise ValueError("Unknown policy type")
+
+
+def mcts_plan(env, episodes, horizon, gamma, temperature, np_random,
+              prior_policy=None, rollout_policy=None):
+    """MCTS.plan (mcts.py:179-184) from a fresh root.  Returns (plan, tree)."""
+    prior_policy = prior_policy or {"type": "random_available"}
+    rollout_policy = rollout_policy or {"type": "random_available"}
+    t = Tree()
+    t.value, t.prior = [], []
+
+    def new_node(parent, action, depth, prior):
+        t.parent.append(parent)
+        t.action.append(action)
+        t.depth.append(depth)
+        t.count.append(0)                                       # abstract.py:231
+        t.first_child.append(-1)
+        t.n_children.append(0)
+        t.value.append(0.0)
+        t.prior.append(prior)
+        return len(t.parent) - 1
+
+    new_node(-1, -1, 0, 1)
+    for _ in range(episodes):
+        state = copy.deepcopy(env)                              # :183
+        node, total, depth, terminal = 0, 0, 0, False
+        while depth < horizon and t.n_children[node] > 0 and not terminal:   # :141
+            kids = list(t.children(node))
+            # selection_strategy (:275-286)
+            x = np.array([t.value[c] + temperature * len(kids) * t.prior[c] / (t.count[c] + 1)
+                          for c in kids])
+            indices = np.nonzero(x == np.amax(x))[0]
+            child = kids[np_random.choice(indices)]             # random_argmax
+            _, reward, terminal, _, _ = state.step(t.action[child])
+            total += gamma ** depth * reward
+            node = child
+            depth += 1
+        if t.n_children[node] == 0 and depth < horizon and (not terminal or node == 0):   # :151-154
+            actions, probs = _policy(prior_policy, state)
+            t.first_child[node] = len(t.parent)
+            t.n_children[node] = len(actions)
+            for a, p in zip(actions, probs):
+                new_node(node, int(a), depth + 1, p)
+        if not terminal:                                        # :156-157, evaluate :160-177
+            for h in range(depth, horizon):
+                actions, probs = _policy(rollout_policy, state)
+                a = np_random.choice(actions, 1, p=np.array(probs))[0]
+                _, reward, term, trunc, _ = state.step(a)
+                total += gamma ** h * reward
+                if np.all(term) or np.all(trunc):
+                    break
+        n = node                                                # update_branch :257-265
+        while n >= 0:
+            t.count[n] += 1
+            t.value[n] += 1.0 / t.count[n] * (total - t.value[n])
+            n = t.parent[n]
+    # get_plan with MCTSNode.selection_rule (:212-218)
+    plan, node = [], 0
+    while t.n_children[node] > 0:
+        kids = list(t.children(node))
+        counts = np.array([t.count[c] for c in kids])
+        ties = np.nonzero(counts == np.amax(counts))[0]
+        best = max(ties, key=lambda i: t.value[kids[i]])
+        plan.append(t.action[kids[best]])
+        node = kids[best]
+    return plan, t
+
+
+# --------------------------------------------------------------------------
+# KL-UCB -- rl_agents/utils.py:89-203
+# --------------------------------------------------------------------------
+def bernoulli_kl(p, q):
+    # utils.py:89-106
+    kl1, kl2 = 0, math.inf
+    if p > 0:
+        if q > 0:
+            kl1 = p * np.log(p / q)
+    if q < 1:
+        if p < 1:
+            kl2 = (1 - p) * np.log((1 - p) / (1 - q))
+        else:
+            kl2 = 0
+    return kl1 + kl2
+
+
+def kl_upper_bound(_sum, count, threshold=1, eps=1e-2):
+    """utils.py:123-147 + newton_iteration (:150-203), upper bound only."""
+    if count == 0:
+        return 1
+    mu = _sum / count
+    max_div = threshold / count
+    a, b = mu, 1
+    x = math.inf
+    if a == b:
+        return a
+    x_next = (a + b) / 2
+    iterations = 0
+    while abs(x - x_next) > eps and iterations < 100:
+        iterations += 1
+        x = x_next
+        f_x = bernoulli_kl(mu, x) - max_div
+        try:
+            df_x = (1 - mu) / (1 - x) - mu / x
+        except ZeroDivisionError:
+            df_x = (f_x - (bernoulli_kl(mu, x - eps) - max_div)) / eps
+        if df_x != 0:
+            x_next = x - f_x / df_x
+        if x_next < a:
+            x_next = 0.9 * a + (1 - 0.9) * x
+        elif x_next > b:
+            x_next = 0.9 * b + (1 - 0.9) * x
+    if x_next < a:
+        x_next = a
+    if x_next > b:
+        x_next = b
+    return x_next
+
+
+# --------------------------------------------------------------------------
+# OLOP / KL-OLOP -- rl_agents/agents/tree_search/olop.py
+# --------------------------------------------------------------------------
+def olop_plan(env, budget, gamma, np_random, upper_bound=None,
+              continuation_type="zeros", episodes=None, horizon=None):
+    """OLOP.plan (olop.py:94-100) from reset (:36-40).  `env.step` follows the
+    legacy 4-tuple API olop.py:87 expects.  Returns (plan, tree)."""
+    upper_bound = upper_bound or {"type": "hoeffding", "time": "global",
+                                  "threshold": "4*np.log(time)"}
+    if horizon is None:
+        budget = max(env.action_space.n, budget)                # :46-48
+        episodes, horizon = olop_allocation(budget, gamma)
+    kl = upper_bound["type"] == "kullback-leibler"
+    t = Tree()
+    t.cumulative_reward, t.mu_ucb, t.upper, t.done = [], [], [], []
+
+    def new_node(parent, action, depth):
+        # OLOPNode.__init__ (:106-124)
+        t.parent.append(parent)
+        t.action.append(action)
+        t.depth.append(depth)
+        t.count.append(0)
+        t.first_child.append(-1)
+        t.n_children.append(0)
+        t.cumulative_reward.append(0)
+        t.mu_ucb.append(1 if kl else math.inf)
+        t.upper.append((1 - gamma ** (horizon + 1 - depth)) / (1 - gamma))
+        t.done.append(False)
+        return len(t.parent) - 1
+
+    new_node(-1, -1, 0)
+    for episode in range(episodes):
+        state = copy.deepcopy(env)
+        state.seed(np_random.randint(2 ** 30))                  # :73
+        node = 0
+        for h in range(horizon):
+            if t.n_children[node] == 0:                         # :78-82
+                actions = _available_actions(state)
+                t.first_child[node] = len(t.parent)
+                t.n_children[node] = len(actions)
+                for a in actions:
+                    new_node(node, a, t.depth[node] + 1)
+                if continuation_type == "uniform":
+                    action = np_random.choice(list(actions))
+                else:
+                    action = 0
+                child = next(c for c in t.children(node) if t.action[c] == action)
+            else:                                               # :84 first max
+                child = t.first_child[node]
+                for c in t.children(node):
+                    if t.upper[c] > t.upper[child]:
+                        child = c
+                action = t.action[child]
+            _, reward, done, _ = state.step(action)             # :87
+            node = child
+            # update (:132-142)
+            if not 0 <= reward <= 1:
+                raise ValueError("This planner assumes that all rewards are normalized in [0, 1]")
+            if done:
+                t.done[node] = True
+            if t.done[node]:
+                reward = 0
+            t.cumulative_reward[node] += reward
+            t.count[node] += 1
+            if kl:                                              # :144-163
+                time = (episode + 1) if upper_bound["time"] == "local" else episodes  # noqa: F841
+                threshold = eval(upper_bound["threshold"])
+                t.mu_ucb[node] = kl_upper_bound(t.cumulative_reward[node], t.count[node], threshold)
+        n = node                                                # backup_to_root :182-193
+        while n >= 0:
+            if t.n_children[n] > 0:
+                t.upper[n] = t.mu_ucb[n] + gamma * max(t.upper[c] for c in t.children(n))
+            else:
+                assert t.depth[n] == horizon
+                t.upper[n] = t.mu_ucb[n]
+            n = t.parent[n]
+    t.episodes, t.horizon = episodes, horizon
+    # get_plan with OLOPNode.selection_rule (:126-130)
+    plan, node = [], 0
+    while t.n_children[node] > 0:
+        kids = list(t.children(node))
+        counts = np.array([t.count[c] for c in kids])
+        ties = np.nonzero(counts == np.amax(counts))[0]
+        best = max(ties, key=lambda i: t.upper[kids[i]])
+        plan.append(t.action[kids[best]])
+        node = kids[best]
+    return plan, t
+
+
+# --------------------------------------------------------------------------
+# Value iteration -- rl_agents/agents/dynamic_programming/value_iteration.py
+# --------------------------------------------------------------------------
+def bellman_expectation(mode, transition, reward, terminal, value, gamma, nxt=None):
+    # value_iteration.py:51-63
+    if mode == "deterministic":
+        next_v = value[transition]
+    elif mode == "stochastic":
+        next_v = (transition * value.reshape((1, 1, value.size))).sum(axis=-1)
+    elif mode == "sparse":
+        next_v = (transition * np.take(value, nxt)).sum(axis=-1)
+    else:
+        raise ValueError("Unknown mode")
+    next_v[terminal] = 0
+    return reward + gamma * next_v
+
+
+def value_iteration(mode, transition, reward, terminal, gamma, iterations, nxt=None):
+    """get_state_action_value + fixed_point_iteration (value_iteration.py:42-45,
+    65-73): iterates on Q; on np.allclose returns the PREVIOUS iterate."""
+    q = np.zeros(reward.shape)
+    sweeps = 0
+    for _ in range(iterations):
+        sweeps += 1
+        nq = bellman_expectation(mode, transition, reward, terminal, q.max(axis=-1), gamma, nxt)
+        if np.allclose(q, nq):
+            break
+        q = nq
+    return q, sweeps

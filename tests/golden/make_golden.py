@@ -1,0 +1,261 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED
+reference (/root/reference) on the oracle env models.
+
+Build-container only (the reference tree does not travel to the GPU box);
+the outputs are committed.  Usage:  python tests/golden/make_golden.py
+"""
+import copy
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_loader  # noqa: E402
+from oracle import envs  # noqa: E402
+
+ref_loader.load_reference()
+from rl_agents.agents.tree_search import deterministic as ref_det  # noqa: E402
+from rl_agents.agents.tree_search import mcts as ref_mcts  # noqa: E402
+from rl_agents.agents.tree_search import olop as ref_olop  # noqa: E402
+from rl_agents.agents.tree_search import abstract as ref_abs  # noqa: E402
+from rl_agents.agents.dynamic_programming import value_iteration as ref_vi  # noqa: E402
+from rl_agents import utils as ref_utils  # noqa: E402
+
+CREATED = []
+
+
+def _instrument(cls):
+    """Record node creation order at run time (sources stay unmodified)."""
+    orig = cls.__init__
+
+    def init(self, *a, **k):
+        orig(self, *a, **k)
+        CREATED.append(self)
+    cls.__init__ = init
+
+
+for _cls in (ref_det.DeterministicNode, ref_mcts.MCTSNode, ref_olop.OLOPNode):
+    _instrument(_cls)
+
+
+def dump_tree(fields, root):
+    # the planner builds a throw-away root in __init__ and again on
+    # step_by_reset (abstract.py:113-114,189-193): keep the final tree only
+    def top(n):
+        while n.parent is not None:
+            n = n.parent
+        return n
+    CREATED[:] = [n for n in CREATED if top(n) is root]
+    assert CREATED[0] is root
+    ids = {id(n): i for i, n in enumerate(CREATED)}
+    out = {"parent": [], "action": [], "count": []}
+    for f in fields:
+        out[f] = []
+    for n in CREATED:
+        out["parent"].append(ids[id(n.parent)] if n.parent is not None else -1)
+        act = -1
+        if n.parent is not None:
+            for a, c in n.parent.children.items():
+                if c is n:
+                    act = int(a)
+        out["action"].append(act)
+        out["count"].append(int(n.count))
+        for f in fields:
+            v = getattr(n, f)
+            out[f].append(bool(v) if isinstance(v, (bool, np.bool_)) else float(v))
+    return out
+
+
+def summarize(tree, full):
+    if full:
+        return tree
+    keep = {k: v[:64] for k, v in tree.items()}
+    keep["n_nodes"] = len(tree["parent"])
+    for k, v in tree.items():
+        if k in ("lower", "upper", "value", "reward", "cumulative_reward", "mu_ucb"):
+            keep["sum_" + k] = float(np.sum(np.asarray(v, dtype=np.float64)))
+        elif k in ("parent", "action", "count"):
+            keep["sum_" + k] = int(np.sum(np.asarray(v, dtype=np.int64)))
+            keep["wsum_" + k] = int(np.sum(np.asarray(v, dtype=np.int64) * (np.arange(len(v)) % 1009)))
+    return keep
+
+
+def run_opd(env, budget, gamma, seed=0, full=True):
+    del CREATED[:]
+    agent = ref_det.DeterministicPlannerAgent(env, {"budget": budget, "gamma": gamma})
+    agent.seed(seed)
+    t0 = time.perf_counter()
+    plan = agent.plan(None)
+    dt = time.perf_counter() - t0
+    for n in CREATED:
+        n.lower, n.upper = n.value_lower, n.value_upper
+    tree = dump_tree(["reward", "lower", "upper", "done"], agent.planner.root)
+    return {"budget": budget, "gamma": gamma, "seed": seed, "plan": [int(a) for a in plan],
+            "n_leaves": len(agent.planner.leaves), "seconds": dt,
+            "tree": summarize(tree, full)}
+
+
+def run_mcts(env, config, seed=0, full=True):
+    del CREATED[:]
+    agent = ref_mcts.MCTSAgent(env, dict(config))
+    agent.seed(seed)
+    t0 = time.perf_counter()
+    plan = agent.plan(None)
+    dt = time.perf_counter() - t0
+    tree = dump_tree(["value", "prior"], agent.planner.root)
+    return {"config": config, "seed": seed, "plan": [int(a) for a in plan],
+            "episodes": int(agent.planner.config["episodes"]),
+            "horizon": int(agent.planner.config["horizon"]),
+            "temperature": float(agent.planner.config["temperature"]),
+            "seconds": dt, "tree": summarize(tree, full)}
+
+
+def run_olop(env, config, seed=0, full=True):
+    del CREATED[:]
+    agent = ref_olop.OLOPAgent(envs.LegacyStepEnv(env), dict(config))
+    agent.planner.np_random, _ = ref_loader.legacy_np_random(seed)
+    plan = agent.plan(None)
+    for n in CREATED:
+        n.upper = n.value_upper
+    tree = dump_tree(["cumulative_reward", "mu_ucb", "upper", "done"], agent.planner.root)
+    return {"config": config, "seed": seed, "plan": [int(a) for a in plan],
+            "episodes": int(agent.planner.config["episodes"]),
+            "horizon": int(agent.planner.config["horizon"]),
+            "tree": summarize(tree, full)}
+
+
+def run_vi(mdp_env, gamma, iterations):
+    agent = ref_vi.ValueIterationAgent(mdp_env, {"gamma": gamma, "iterations": iterations})
+    q = agent.state_action_value
+    return {"gamma": gamma, "iterations": iterations, "q": q.tolist(),
+            "act0": int(agent.act(0)) if True else None}
+
+
+def load_json_mdp(path):
+    with open(path) as f:
+        cfg = json.load(f)
+    return (np.array(cfg["transition"]), np.array(cfg["reward"], dtype=np.float64),
+            np.array(cfg.get("terminal", [0] * len(cfg["reward"]))).astype(bool), cfg["mode"])
+
+
+def main():
+    cfg_dir = os.path.join(ref_loader.REFERENCE_ROOT, "scripts/configs/FiniteMDPEnv")
+    out = {}
+
+    # ---------------- finite MDP fixtures (inputs) ----------------
+    T, R, term, mode = load_json_mdp(os.path.join(cfg_dir, "large/env_1.json"))
+    T2, R2, term2, _ = load_json_mdp(os.path.join(cfg_dir, "large/env_2.json"))
+    Tt, Rt, termt, _ = load_json_mdp(os.path.join(cfg_dir, "trap/env_1.json"))
+    Tl, Rl, terml, _ = load_json_mdp(os.path.join(cfg_dir, "env_loop.json"))
+    np.savez_compressed(os.path.join(HERE, "finite_mdps.npz"),
+                        large1_T=T, large1_R=R, large1_term=term,
+                        large2_T=T2, large2_R=R2, large2_term=term2,
+                        trap_T=Tt, trap_R=Rt, trap_term=termt,
+                        loop_T=Tl, loop_R=Rl, loop_term=terml)
+
+    def finite(Tm=T, Rm=R, tm=term):
+        return envs.FiniteMDPLite(Tm, Rm, tm, mode="deterministic", state=0)
+
+    # ---------------- VI ----------------
+    vi = {}
+    vi["large1_g0.9_it100"] = run_vi(finite(), 0.9, 100)
+    vi["large1_g1.0_it2"] = run_vi(finite(), 1.0, 2)
+    vi["trap_g0.9_it100"] = run_vi(finite(Tt, Rt, termt), 0.9, 100)
+    vi["loop_g0.9_it100"] = run_vi(finite(Tl, Rl, terml), 0.9, 100)
+    # dense stochastic + sparse, C1-shaped: seed 0, S=100, A=4
+    rng = np.random.default_rng(0)
+    P = rng.uniform(size=(100, 4, 100)); P /= P.sum(-1, keepdims=True)
+    Rd = rng.uniform(size=(100, 4))
+    env_d = envs.FiniteMDPLite(P, Rd, None, mode="stochastic")
+    vi["dense_c1_g0.95_it100"] = run_vi(env_d, 0.95, 100)
+    Ps, Ns, Rs = envs.garnet(500, 4, 3, seed=1)
+    terms = np.zeros(500, bool); terms[::37] = True
+    env_s = envs.FiniteMDPLite(Ps, Rs, terms, mode="sparse", nxt=Ns)
+    vi["sparse_garnet500_g0.95_it100"] = run_vi(env_s, 0.95, 100)
+    out["vi"] = vi
+
+    # ---------------- OPD on finite ----------------
+    opd = {}
+    opd["large1_b500_g0.9"] = run_opd(finite(), 500, 0.9)
+    opd["large1_b75_g0.7"] = run_opd(finite(), 75, 0.7)
+    opd["large1_b10000_g0.9"] = run_opd(finite(), 10000, 0.9, full=False)
+    opd["large2_b2000_g0.8"] = run_opd(finite(T2, R2, term2), 2000, 0.8, full=False)
+    # terminal states + terminal_reward path: mark a few states terminal
+    termx = term.copy(); termx[[3, 17, 66, 91]] = True
+    opd["large1_terminal_b300_g0.85"] = run_opd(finite(T, R, termx), 300, 0.85)
+    out["opd"] = opd
+
+    # ---------------- MCTS on finite ----------------
+    mc = {}
+    mc["large1_b10000_g0.9"] = run_mcts(finite(), {"budget": 10000, "gamma": 0.9}, full=False)
+    mc["large1_b400_g0.8"] = run_mcts(finite(), {"budget": 400, "gamma": 0.8})
+    mc["large1_ep200_h12_g0.95_T5"] = run_mcts(
+        finite(), {"episodes": 200, "horizon": 12, "gamma": 0.95, "temperature": 5.0}, seed=3)
+    mc["large1_terminal_b600_g0.9"] = run_mcts(finite(T, R, termx), {"budget": 600, "gamma": 0.9}, seed=1)
+    out["mcts"] = mc
+
+    # ---------------- OLOP (KL) on finite ----------------
+    ol = {}
+    kl_cfg = {"budget": 200, "gamma": 0.9, "continuation_type": "uniform",
+              "upper_bound": {"type": "kullback-leibler", "time": "global", "threshold": "2*np.log(time)"}}
+    ol["large1_b200_g0.9_uniform"] = run_olop(finite(), kl_cfg)
+    kl_cfg2 = {"budget": 500, "gamma": 0.7, "continuation_type": "zeros",
+               "upper_bound": {"type": "kullback-leibler", "time": "local", "threshold": "1*np.log(time)"}}
+    ol["large1_b500_g0.7_zeros_local"] = run_olop(finite(), kl_cfg2, seed=2)
+    out["olop"] = ol
+    out["allocation"] = {"%d_%g" % (b, g): list(ref_olop.OLOP.allocation(b, g))
+                         for b, g in [(100, .8), (400, .8), (500, .7), (600, .8), (10000, .8),
+                                      (10000, .9), (81920, .8)]}
+    out["kl_upper_bound"] = [
+        [s, c, th, float(ref_utils.kl_upper_bound(s, c, th, eps=1e-3))]
+        for s, c, th in [(0.5, 1, float(np.log(10))), (5, 10, float(np.log(20))), (10, 20, float(np.log(40)))]]
+    out["kl_upper_bound_eps1e-2"] = [
+        [s, c, th, float(ref_utils.kl_upper_bound(s, c, th))]
+        for s, c, th in [(0.5, 1, 2.0), (3.25, 7, 5.5), (0, 4, 3.0), (4, 4, 3.0), (17.5, 40, 9.2)]]
+    with open(os.path.join(HERE, "golden_finite.json"), "w") as f:
+        json.dump(out, f)
+    print("finite done")
+
+    # ---------------- HighwayLite ----------------
+    hw = {"states": {}, "traces": {}, "opd": {}, "mcts": {}}
+    for seed in range(6):
+        hw["states"][str(seed)] = envs.make_highway_state(seed).pack().tolist()
+    # env traces: random available actions, full state words after each step
+    for seed in range(8):
+        env = envs.HighwayLite(seed=seed)
+        rng = np.random.default_rng(100 + seed)
+        steps = []
+        for _ in range(45):
+            avail = env.get_available_actions()
+            # mostly IDLE so that the trace survives long enough to exercise
+            # IDM / MOBIL / truncation, with random lane/speed changes mixed in
+            if seed < 4:
+                a = 1 if rng.uniform() < 0.7 else int(avail[rng.integers(len(avail))])
+            else:   # slow ego: traffic queues behind it, episode reaches truncation
+                a = 4 if 4 in avail else 1
+            _, r, term_, trunc, _ = env.step(a)
+            steps.append({"a": a, "avail": [int(x) for x in avail], "r": float(r), "term": bool(term_),
+                          "trunc": bool(trunc), "state": env.state.pack().tolist()})
+            if term_:
+                break
+        hw["traces"][str(seed)] = steps
+    hw["opd"]["s0_b75_g0.7"] = run_opd(envs.HighwayLite(seed=0), 75, 0.7)
+    hw["opd"]["s1_b300_g0.8"] = run_opd(envs.HighwayLite(seed=1), 300, 0.8)
+    hw["opd"]["s2_b1000_g0.8"] = run_opd(envs.HighwayLite(seed=2), 1000, 0.8, full=False)
+    hw["mcts"]["s0_ep60_h6_g0.8"] = run_mcts(envs.HighwayLite(seed=0),
+                                              {"episodes": 60, "horizon": 6, "gamma": 0.8}, seed=0)
+    hw["mcts"]["s3_b200_g0.8"] = run_mcts(envs.HighwayLite(seed=3), {"budget": 200, "gamma": 0.8}, seed=5)
+    if "--big" in sys.argv:
+        hw["opd"]["s0_b10000_g0.8"] = run_opd(envs.HighwayLite(seed=0), 10000, 0.8, full=False)
+    with open(os.path.join(HERE, "golden_highway.json"), "w") as f:
+        json.dump(hw, f)
+    print("highway done")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,155 @@
+"""Pin the oracle restatements (oracle/planners.py, oracle/envs.py) against
+golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py) and against the reference's own known answers
+(tests/agents/test_utils.py:28-31 of the reference)."""
+import numpy as np
+import pytest
+
+from oracle import envs, planners, ref_loader
+from tests.util import assert_tree_matches, load_golden, load_mdps
+
+G = load_golden("golden_finite.json")
+H = load_golden("golden_highway.json")
+M = load_mdps()
+
+
+def np_random(seed):
+    return np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+
+
+def finite(name="large1", terminal=None):
+    term = M[name + "_term"] if terminal is None else terminal
+    return envs.FiniteMDPLite(M[name + "_T"], M[name + "_R"], term)
+
+
+def tree_dict(t, fields):
+    d = {"parent": t.parent, "action": t.action, "count": t.count}
+    for f in fields:
+        d[f] = getattr(t, f)
+    return d
+
+
+@pytest.mark.parametrize("key,mdp", [("large1_b500_g0.9", "large1"), ("large1_b75_g0.7", "large1"),
+                                     ("large1_b10000_g0.9", "large1"), ("large2_b2000_g0.8", "large2")])
+def test_opd_finite(key, mdp):
+    g = G["opd"][key]
+    plan, t = planners.opd_plan(finite(mdp), g["budget"], g["gamma"], np_random=np_random(g["seed"]))
+    assert plan == g["plan"]
+    assert t.n_leaves == g["n_leaves"]
+    assert_tree_matches(tree_dict(t, ["reward", "lower", "upper", "done"]), g["tree"],
+                        ["reward", "lower", "upper"])
+
+
+def test_opd_finite_terminal():
+    g = G["opd"]["large1_terminal_b300_g0.85"]
+    term = M["large1_term"].copy()
+    term[[3, 17, 66, 91]] = True
+    plan, t = planners.opd_plan(finite(terminal=term), 300, 0.85, np_random=np_random(0))
+    assert plan == g["plan"]
+    assert any(t.done)
+    assert_tree_matches(tree_dict(t, ["reward", "lower", "upper", "done"]), g["tree"],
+                        ["reward", "lower", "upper"])
+
+
+@pytest.mark.parametrize("key", sorted(G["mcts"]))
+def test_mcts_finite(key):
+    g = G["mcts"][key]
+    term = None
+    if "terminal" in key:
+        term = M["large1_term"].copy()
+        term[[3, 17, 66, 91]] = True
+    plan, t = planners.mcts_plan(finite(terminal=term), g["episodes"], g["horizon"], g["config"]["gamma"],
+                                 g["temperature"], np_random(g["seed"]))
+    assert plan == g["plan"]
+    assert_tree_matches(tree_dict(t, ["value", "prior"]), g["tree"], ["value", "prior"])
+
+
+@pytest.mark.parametrize("key", sorted(G["olop"]))
+def test_olop_finite(key):
+    g = G["olop"][key]
+    rng, _ = ref_loader.legacy_np_random(g["seed"])
+    cfg = g["config"]
+    plan, t = planners.olop_plan(envs.LegacyStepEnv(finite()), cfg["budget"], cfg["gamma"], rng,
+                                 upper_bound=cfg["upper_bound"], continuation_type=cfg["continuation_type"])
+    assert (t.episodes, t.horizon) == (g["episodes"], g["horizon"])
+    assert plan == g["plan"]
+    assert_tree_matches(tree_dict(t, ["cumulative_reward", "mu_ucb", "upper", "done"]), g["tree"],
+                        ["cumulative_reward", "mu_ucb", "upper"])
+
+
+def test_allocation_and_kl_known_answers():
+    for key, (ep, hz) in G["allocation"].items():
+        b, gm = key.split("_")
+        assert planners.olop_allocation(int(b), float(gm)) == (ep, hz)
+    # reference tests/agents/test_utils.py:29-31 (abs 1e-3)
+    assert planners.kl_upper_bound(0.5, 1, np.log(10), eps=1e-3) == pytest.approx(0.997, abs=1e-3)
+    assert planners.kl_upper_bound(5, 10, np.log(20), eps=1e-3) == pytest.approx(0.835, abs=1e-3)
+    assert planners.kl_upper_bound(10, 20, np.log(40), eps=1e-3) == pytest.approx(0.777, abs=1e-3)
+    for s, c, th, ref in G["kl_upper_bound"]:
+        assert planners.kl_upper_bound(s, c, th, eps=1e-3) == ref
+    for s, c, th, ref in G["kl_upper_bound_eps1e-2"]:
+        assert planners.kl_upper_bound(s, c, th) == ref
+
+
+def test_value_iteration():
+    def run(name, gamma, it):
+        q, _ = planners.value_iteration("deterministic", M[name + "_T"], M[name + "_R"], M[name + "_term"],
+                                        gamma, it)
+        return q
+    for key, name in [("large1_g0.9_it100", "large1"), ("large1_g1.0_it2", "large1"),
+                      ("trap_g0.9_it100", "trap"), ("loop_g0.9_it100", "loop")]:
+        g = G["vi"][key]
+        assert np.array_equal(run(name, g["gamma"], g["iterations"]), np.array(g["q"])), key
+    # SURVEY appendix C anchors
+    q = np.array(G["vi"]["large1_g0.9_it100"]["q"])
+    assert q[0].tolist() == [8.586584113252275, 8.332319959947995, 8.33806448333072, 8.876425018786213,
+                             8.505965200730994]
+    assert q.sum() == 4193.544746115075
+    rng = np.random.default_rng(0)
+    P = rng.uniform(size=(100, 4, 100))
+    P /= P.sum(-1, keepdims=True)
+    R = rng.uniform(size=(100, 4))
+    q, _ = planners.value_iteration("stochastic", P, R, np.zeros(100, bool), 0.95, 100)
+    assert np.array_equal(q, np.array(G["vi"]["dense_c1_g0.95_it100"]["q"]))
+    Ps, Ns, Rs = envs.garnet(500, 4, 3, seed=1)
+    term = np.zeros(500, bool)
+    term[::37] = True
+    q, _ = planners.value_iteration("sparse", Ps, Rs, term, 0.95, 100, nxt=Ns)
+    assert np.array_equal(q, np.array(G["vi"]["sparse_garnet500_g0.95_it100"]["q"]))
+
+
+# ------------------------- HighwayLite -------------------------
+def test_highway_scene_and_traces_are_reproducible():
+    for seed, words in H["states"].items():
+        assert envs.make_highway_state(int(seed)).pack().tolist() == words
+    for seed, steps in H["traces"].items():
+        env = envs.HighwayLite(seed=int(seed))
+        for st in steps[:12]:
+            assert env.get_available_actions() == st["avail"]
+            _, r, term, trunc, _ = env.step(st["a"])
+            assert (r, term, trunc) == (st["r"], st["term"], st["trunc"])
+            assert env.state.pack().tolist() == st["state"]
+
+
+def test_highway_pack_roundtrip():
+    s = envs.make_highway_state(3)
+    s2 = envs.HighwayLiteState.unpack(s.pack())
+    assert s2.pack().tolist() == s.pack().tolist()
+
+
+@pytest.mark.parametrize("key", ["s0_b75_g0.7", "s1_b300_g0.8"])
+def test_opd_highway(key):
+    g = H["opd"][key]
+    seed = int(key[1])
+    plan, t = planners.opd_plan(envs.HighwayLite(seed=seed), g["budget"], g["gamma"], np_random=np_random(0))
+    assert plan == g["plan"]
+    assert_tree_matches(tree_dict(t, ["reward", "lower", "upper", "done"]), g["tree"],
+                        ["reward", "lower", "upper"])
+
+
+def test_mcts_highway():
+    g = H["mcts"]["s0_ep60_h6_g0.8"]
+    plan, t = planners.mcts_plan(envs.HighwayLite(seed=0), g["episodes"], g["horizon"], 0.8,
+                                 g["temperature"], np_random(0))
+    assert plan == g["plan"]
+    assert_tree_matches(tree_dict(t, ["value", "prior"]), g["tree"], ["value", "prior"])

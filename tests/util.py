@@ -1,0 +1,59 @@
+"""Shared helpers of the parity tests: golden loading and tree comparison."""
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def load_mdps():
+    return np.load(os.path.join(GOLDEN, "finite_mdps.npz"))
+
+
+def tree_summary(tree):
+    """Same digest as tests/golden/make_golden.py::summarize (non-full)."""
+    out = {"n_nodes": len(tree["parent"])}
+    for k, v in tree.items():
+        if k in ("lower", "upper", "value", "reward", "cumulative_reward", "mu_ucb"):
+            out["sum_" + k] = float(np.sum(np.asarray(v, dtype=np.float64)))
+        elif k in ("parent", "action", "count"):
+            a = np.asarray(v, dtype=np.int64)
+            out["sum_" + k] = int(a.sum())
+            out["wsum_" + k] = int((a * (np.arange(len(a)) % 1009)).sum())
+    return out
+
+
+def assert_tree_matches(got, golden, float_fields, exact=True, rtol=0.0, atol=0.0):
+    """`got`: dict of equal-length sequences; `golden`: a golden tree, either
+    full or the digest form (first 64 nodes + sums)."""
+    full = "n_nodes" not in golden
+    n = len(golden["parent"]) if full else golden["n_nodes"]
+    assert len(got["parent"]) == n
+    k = n if full else 64
+    for f in ("parent", "action", "count"):
+        assert [int(x) for x in got[f][:k]] == [int(x) for x in golden[f][:k]], f
+    for f in float_fields:
+        a = np.asarray(got[f][:k], dtype=np.float64)
+        b = np.asarray(golden[f][:k], dtype=np.float64)
+        if exact:
+            assert np.array_equal(a, b), (f, np.abs(a - b).max())
+        else:
+            np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=f)
+    if "done" in golden and "done" in got:
+        assert [bool(x) for x in got["done"][:k]] == [bool(x) for x in golden["done"][:k]]
+    if not full:
+        s = tree_summary({f: got[f] for f in list(float_fields) + ["parent", "action", "count"]})
+        for key, val in s.items():
+            if key.startswith("sum_") and key[4:] in float_fields:
+                if exact:
+                    assert val == golden[key], key
+                else:
+                    np.testing.assert_allclose(val, golden[key], rtol=max(rtol, 1e-12), err_msg=key)
+            elif key != "n_nodes":
+                assert val == golden[key], key
