@@ -1,0 +1,197 @@
+/*
+ * b2_planner.h -- C ABI of libb2planner.so, the B200 (sm_100a) planning engine
+ * behind the rl-agents plugin surface.
+ *
+ * Every entry point replaces the inner loop of one reference method (cited as
+ * file:line under /root/reference).  Conventions:
+ *   - plain C, no allocation, no ownership: every buffer is caller-owned device
+ *     memory (e.g. torch.Tensor.data_ptr()) unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; calls enqueue work and return
+ *     without synchronising; the caller synchronises before reading results;
+ *   - return 0 on success, otherwise a non-zero code; b2_last_error() gives the
+ *     message for the calling thread;
+ *   - distinct handles / buffers are independent: safe from different host
+ *     threads or processes (scripts/experiments.py:105 forks worker processes).
+ */
+#ifndef B2_PLANNER_H
+#define B2_PLANNER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_INVALID 1   /* bad argument */
+#define B2_ERR_CUDA 2      /* CUDA runtime error, see b2_last_error() */
+#define B2_ERR_UNSUPPORTED 3
+
+const char* b2_last_error(void);
+int b2_version(void);
+/* number of SMs / device name of the current device (diagnostics for bench.py) */
+int b2_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+
+/* ------------------------------------------------------------------------
+ * Environment models (the batched transition the planners call)
+ * ---------------------------------------------------------------------- */
+#define B2_ENV_FINITE 0   /* deterministic finite MDP tables               */
+#define B2_ENV_HIGHWAY 1  /* HighwayLite, docs/HIGHWAY_LITE_SPEC.md         */
+
+#define B2_HW_STATE_WORDS 136 /* 32-bit words of one HighwayLite state      */
+#define B2_HW_ACTIONS 5
+
+typedef struct b2_finite_mdp {
+    int32_t n_states;
+    int32_t n_actions;
+    const int32_t* transition; /* [S, A] next state (deterministic mode)     */
+    const double* reward;      /* [S, A]                                     */
+    const uint8_t* terminal;   /* [S]                                        */
+} b2_finite_mdp;
+
+/* One decision step of n_envs HighwayLite states (15 physics sub-steps each).
+ * Replaces `env.step(a)` on a deep-copied env: deterministic.py:36-43,
+ * mcts.py:145,173.  states: [n_envs, 136] words, updated in place.
+ * actions: [n_envs] int32.  reward: [n_envs] float; flags: [n_envs] int32,
+ * bit0 terminated, bit1 truncated.  avail_mask (nullable): [n_envs] int32
+ * bitmask of get_available_actions() in the NEW state. */
+int b2_highway_step(int32_t* states, const int32_t* actions, float* reward, int32_t* flags,
+                    int32_t* avail_mask, int32_t n_envs, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Value iteration -- rl_agents/agents/dynamic_programming/value_iteration.py
+ * ---------------------------------------------------------------------- */
+#define B2_VI_DETERMINISTIC 0 /* next_v = V[T]                (:52-53)       */
+#define B2_VI_STOCHASTIC 1    /* next_v = sum_s' P[s,a,s']V[s'] (:54-55)     */
+#define B2_VI_SPARSE 2        /* next_v = sum_b P[s,a,b]V[N[s,a,b]] (:56-59) */
+
+typedef struct b2_vi_problem {
+    int32_t mode;
+    int32_t n_actions;   /* A                                                */
+    int32_t n_next;      /* B (sparse), S (stochastic), ignored otherwise    */
+    int32_t reserved;
+    int64_t n_states;    /* S of the whole MDP (length of V)                 */
+    int64_t row_begin;   /* state slab [row_begin, row_end) owned by the call */
+    int64_t row_end;
+    double gamma;
+    double rtol, atol;   /* np.allclose tolerances (1e-5, 1e-8)              */
+    /* slab-local tables: row 0 is state row_begin */
+    const void* transition; /* int32 [rows,A] | double [rows,A,S] | double [rows,A,B] */
+    const int32_t* next;    /* int32 [rows,A,B] (sparse only)                */
+    const double* reward;   /* [rows, A]                                     */
+    const uint8_t* terminal;/* [rows]                                        */
+} b2_vi_problem;
+
+/* One Bellman sweep  Q' = R + gamma * E[V(s')]  fused with V' = max_a Q' and the
+ * np.allclose(Q, Q') test of fixed_point_iteration (value_iteration.py:51-63,
+ * 65-73).  v_in/v_out: [S] (v_out rows of the slab are written); q_old/q_new:
+ * slab-local [rows, A].  viol: int32 [>= sweep_index+1] device counters,
+ * zero-initialised by the caller: the sweep adds the number of elements that
+ * break allclose to viol[sweep_index]; if sweep_index > 0 and
+ * viol[sweep_index-1] == 0 (previous sweep converged) the launch does nothing,
+ * so a whole fixed-point loop can be enqueued without a host round trip. */
+int b2_vi_sweep(const b2_vi_problem* p, const double* v_in, const double* q_old, double* q_new,
+                double* v_out, int32_t* viol, int32_t sweep_index, void* stream);
+
+/* get_state_action_value (value_iteration.py:42-45): `iterations` sweeps
+ * ping-ponging q[0]/q[1] and v[0]/v[1] (q[0], v[0] must hold the initial
+ * zeros).  After synchronising, the first k with viol[k]==0 marks convergence:
+ * the result (the OLD iterate, :70-72) is q[k%2]; without one it is
+ * q[iterations%2].  Single device (row slab = all states). */
+int b2_vi_solve(const b2_vi_problem* p, double* q0, double* q1, double* v0, double* v1,
+                int32_t* viol, int32_t iterations, void* stream);
+
+/* ------------------------------------------------------------------------
+ * OPD -- rl_agents/agents/tree_search/deterministic.py
+ * A batch of n_trees independent decisions, one tree per CTA, strict
+ * best-first order inside each tree (bit-exact node order).
+ * ---------------------------------------------------------------------- */
+typedef struct b2_opd_config {
+    int32_t env_kind;       /* B2_ENV_*                                      */
+    int32_t n_trees;
+    int32_t n_actions;      /* action_space.n: budget divisor (:118) and max branching */
+    int32_t n_expansions;   /* budget // n_actions (:118)                    */
+    int32_t node_capacity;  /* per tree, >= 1 + n_expansions * n_actions     */
+    int32_t plan_capacity;  /* per tree, >= n_expansions + 1                 */
+    int32_t keys_in_smem;   /* 1: frontier keys in shared memory when they fit */
+    int32_t reserved;
+    double terminal_reward; /* config["terminal_reward"] (:60-63)            */
+    const double* gamma_pow;     /* [n_expansions+2] gamma**d   (host floats) */
+    const double* gamma_pow_div; /* [n_expansions+2] gamma**d / (1 - gamma)   */
+    b2_finite_mdp mdp;      /* env_kind == FINITE                            */
+} b2_opd_config;
+
+/* Node arrays, each [n_trees, node_capacity] (struct-of-arrays in HBM) */
+typedef struct b2_opd_tree {
+    int32_t* parent;       /* -1 for the root                                */
+    int32_t* first_child;  /* -1 for a leaf                                  */
+    int32_t* depth;
+    int32_t* count;        /* DeterministicNode.count (:18,:64-65)           */
+    int32_t* meta;         /* action | n_children << 8 | done << 16          */
+    double* reward;
+    double* lower;         /* value_lower                                    */
+    double* upper;         /* value_upper                                    */
+    int32_t* state;        /* FINITE: [n_trees, cap] state ids;
+                              HIGHWAY: [n_trees, cap, 136] words             */
+} b2_opd_tree;
+
+#define B2_OPD_RESULT_WORDS 16
+/* per tree int32 result record:
+ * [0] n_nodes [1] n_leaves [2] max_depth [3] terminal_expansions
+ * [4] error (1: reward outside [0,1], deterministic.py:46-47)
+ * [5] plan_len [6] tie_node (-1, or the node where get_plan met a tie that the
+ *     host must break with the planner RNG, abstract.py:304-311) */
+
+/* bytes of scratch the call needs (frontier keys + tournament + expansion order) */
+int64_t b2_opd_workspace_bytes(const b2_opd_config* cfg);
+
+/* OptimisticDeterministicPlanner.plan (:116-122): root_states [n_trees] int32
+ * state ids or [n_trees,136] words.  plan: int8 [n_trees, plan_capacity]
+ * greedy value_lower path (abstract.py:143-156); result: int32
+ * [n_trees, B2_OPD_RESULT_WORDS]. */
+int b2_opd_plan(const b2_opd_config* cfg, const int32_t* root_states, const b2_opd_tree* tree,
+                void* workspace, int8_t* plan, int32_t* result, void* stream);
+
+/* ------------------------------------------------------------------------
+ * MCTS -- rl_agents/agents/tree_search/mcts.py (open loop)
+ * ---------------------------------------------------------------------- */
+typedef struct b2_mcts_config {
+    int32_t env_kind;
+    int32_t n_trees;
+    int32_t n_actions;
+    int32_t episodes;        /* config["episodes"] (:180)                    */
+    int32_t horizon;         /* config["horizon"]                            */
+    int32_t node_capacity;   /* per tree, >= 1 + episodes * n_actions        */
+    int32_t rollout_policy;  /* 0 random_available, 1 random (:46-72)        */
+    int32_t prior_policy;    /* idem, for expansion priors                   */
+    double temperature;      /* config["temperature"] (:127)                 */
+    const double* gamma_pow; /* [horizon+1] gamma**d                         */
+    const double* uniform_cdf; /* [(n_actions+1), n_actions]: row n = cumsum(ones(n)/n)/last,
+                                  the cdf Generator.choice(a, 1, p) searches (host numpy)  */
+    b2_finite_mdp mdp;
+} b2_mcts_config;
+
+typedef struct b2_mcts_tree {
+    int32_t* parent;
+    int32_t* first_child;
+    int32_t* count;        /* MCTSNode.count (:248-255)                      */
+    int32_t* meta;         /* action | n_children << 8                       */
+    double* value;         /* MCTSNode.value                                 */
+    double* prior;
+} b2_mcts_tree;
+
+#define B2_PCG64_STATE_WORDS 6 /* uint64: state hi,lo, inc hi,lo, has_uint32, uinteger */
+#define B2_MCTS_RESULT_WORDS 8
+/* per tree int32 result: [0] n_nodes [1] plan_len [2] env steps taken */
+
+/* MCTS.plan (:179-184) for n_trees independent decisions, strict episode order
+ * inside each tree, consuming each tree's numpy PCG64 stream exactly as
+ * Generator.choice does (abstract.py:304-311, mcts.py:172).  rng: uint64
+ * [n_trees, 6] numpy bit-generator states, advanced in place.  plan: int8 [n_trees, horizon]. */
+int b2_mcts_plan(const b2_mcts_config* cfg, const int32_t* root_states, const b2_mcts_tree* tree,
+                 uint64_t* rng, int8_t* plan, int32_t* result, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2_PLANNER_H */

@@ -1,0 +1,108 @@
+"""ctypes binding of libb2planner.so (include/b2_planner.h).
+
+The CUDA library IS the product: there is no CPU fallback.  Import of this
+module never builds anything; `load()` raises if the library is missing.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libb2planner.so")
+
+c_void_p, c_int, c_int32, c_int64, c_double = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32,
+                                               ctypes.c_int64, ctypes.c_double)
+
+HW_STATE_WORDS = 136
+HW_ACTIONS = 5
+ENV_FINITE, ENV_HIGHWAY = 0, 1
+VI_DETERMINISTIC, VI_STOCHASTIC, VI_SPARSE = 0, 1, 2
+OPD_RESULT_WORDS = 16
+MCTS_RESULT_WORDS = 8
+PCG64_STATE_WORDS = 6
+
+
+class FiniteMDP(ctypes.Structure):
+    _fields_ = [("n_states", c_int32), ("n_actions", c_int32), ("transition", c_void_p),
+                ("reward", c_void_p), ("terminal", c_void_p)]
+
+
+class VIProblem(ctypes.Structure):
+    _fields_ = [("mode", c_int32), ("n_actions", c_int32), ("n_next", c_int32), ("reserved", c_int32),
+                ("n_states", c_int64), ("row_begin", c_int64), ("row_end", c_int64),
+                ("gamma", c_double), ("rtol", c_double), ("atol", c_double),
+                ("transition", c_void_p), ("next", c_void_p), ("reward", c_void_p), ("terminal", c_void_p)]
+
+
+class OPDConfig(ctypes.Structure):
+    _fields_ = [("env_kind", c_int32), ("n_trees", c_int32), ("n_actions", c_int32),
+                ("n_expansions", c_int32), ("node_capacity", c_int32), ("plan_capacity", c_int32),
+                ("keys_in_smem", c_int32), ("reserved", c_int32), ("terminal_reward", c_double),
+                ("gamma_pow", c_void_p), ("gamma_pow_div", c_void_p), ("mdp", FiniteMDP)]
+
+
+class OPDTree(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("parent", "first_child", "depth", "count", "meta", "reward",
+                                        "lower", "upper", "state")]
+
+
+class MCTSConfig(ctypes.Structure):
+    _fields_ = [("env_kind", c_int32), ("n_trees", c_int32), ("n_actions", c_int32), ("episodes", c_int32),
+                ("horizon", c_int32), ("node_capacity", c_int32), ("rollout_policy", c_int32),
+                ("prior_policy", c_int32), ("temperature", c_double), ("gamma_pow", c_void_p),
+                ("uniform_cdf", c_void_p), ("mdp", FiniteMDP)]
+
+
+class MCTSTree(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("parent", "first_child", "count", "meta", "value", "prior")]
+
+
+EXPORTS = {
+    "b2_last_error": (ctypes.c_char_p, []),
+    "b2_version": (c_int, []),
+    "b2_device_info": (c_int, [ctypes.POINTER(c_int)] * 3 + [ctypes.c_char_p, c_int]),
+    "b2_highway_step": (c_int, [c_void_p] * 5 + [c_int32, c_void_p]),
+    "b2_vi_sweep": (c_int, [ctypes.POINTER(VIProblem)] + [c_void_p] * 5 + [c_int32, c_void_p]),
+    "b2_vi_solve": (c_int, [ctypes.POINTER(VIProblem)] + [c_void_p] * 5 + [c_int32, c_void_p]),
+    "b2_opd_workspace_bytes": (c_int64, [ctypes.POINTER(OPDConfig)]),
+    "b2_opd_plan": (c_int, [ctypes.POINTER(OPDConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
+                            c_void_p, c_void_p]),
+    "b2_mcts_plan": (c_int, [ctypes.POINTER(MCTSConfig), c_void_p, ctypes.POINTER(MCTSTree), c_void_p, c_void_p,
+                             c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2Error("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)      # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B2Error("libb2planner error %d: %s" % (rc, load().b2_last_error().decode()))
+
+
+def ptr(t):
+    """data pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,432 @@
+// OPD (optimistic planning for deterministic systems) -- the plan() loop of
+// OptimisticDeterministicPlanner (rl_agents/agents/tree_search/deterministic.py)
+// for a BATCH of independent decisions: one search tree per CTA, the node
+// order inside each tree exactly the reference's (strict best-first).
+//
+// B200-first restructuring of the reference loop (:106-122):
+//   * the frontier `max(self.leaves, key=upper)` (:110, O(n) per expansion,
+//     65 % of the reference's time) becomes a radix-32 tournament tree over
+//     value_upper keyed by node id: select = one descent, update = three
+//     leaf-to-root refreshes.  Python's max() returns the FIRST maximal leaf in
+//     list order, which is creation order = lowest node id: the descent takes
+//     the lowest lane among equal maxima at every level.
+//   * `safe_deepcopy_env` + `env.step` for every child (:36-43) is the batched
+//     transition kernel (finite-MDP table gather, or hw::step with the scene in
+//     registers); child states live in an HBM arena indexed by node id.
+//   * backup_to_root (:74-79) and the count walk (:64-65) never influence which
+//     leaf is expanded (only leaf bounds do, and they are final at creation),
+//     so they leave the sequential loop: one bottom-up pass in reverse
+//     expansion order reproduces value_lower / value_upper / count of every
+//     node exactly (max and integer sums are order independent).
+#include "common.cuh"
+#include "highway_lite.cuh"
+
+namespace b2 {
+
+constexpr int MAX_LEVELS = 6;          // 32^6 nodes
+constexpr int MAX_BRANCH = 8;
+
+struct LevelLayout {
+    int n_levels;                      // keys = level 0
+    int size[MAX_LEVELS];              // entries per level
+    int64_t offset[MAX_LEVELS];        // in doubles, inside smem or the per-tree workspace
+    int in_smem[MAX_LEVELS];
+    int64_t ws_doubles;                // per-tree workspace doubles (global levels)
+    int64_t ws_bytes_per_tree;         // + expansion order
+    int smem_doubles;
+};
+
+struct OpdArgs {
+    b2_opd_config cfg;
+    b2_opd_tree tree;
+    const int32_t* root_states;
+    char* workspace;
+    int8_t* plan;
+    int32_t* result;
+    LevelLayout lay;
+};
+
+struct Tournament {
+    double* lvl[MAX_LEVELS];
+    int size[MAX_LEVELS];
+    int n_levels;
+
+    __device__ __forceinline__ double get(int l, int i) const { return i < size[l] ? lvl[l][i] : -INFINITY; }
+
+    // lowest node id among the leaves of maximal key (warp-collective)
+    __device__ int select(int lane) const {
+        const int top = n_levels - 1;
+        double v = get(top, lane);
+        const double m = warp_max_f64(v);
+        int idx = __ffs(__ballot_sync(0xffffffffu, v == m)) - 1;
+        for (int l = top - 1; l >= 0; --l) {
+            v = get(l, idx * 32 + lane);
+            idx = idx * 32 + __ffs(__ballot_sync(0xffffffffu, v == m)) - 1;
+        }
+        return idx;
+    }
+
+    // refresh the ancestors of key i after it changed (warp-collective)
+    __device__ void update(int i, int lane) {
+        for (int l = 0; l + 1 < n_levels; ++l) {
+            const int g = i >> 5;
+            const double m = warp_max_f64(get(l, g * 32 + lane));
+            if (lane == 0) lvl[l + 1][g] = m;
+            __syncwarp();
+            i = g;
+        }
+    }
+};
+
+struct Shared {
+    int leaf, depth, n_avail, error, done_parent;
+    double lower;
+    int child_action[MAX_BRANCH];
+    int child_done[MAX_BRANCH];
+    double child_reward[MAX_BRANCH];
+};
+
+__device__ __forceinline__ void setup_tournament(Tournament& T, const LevelLayout& lay, double* smem_d, double* ws_d) {
+    T.n_levels = lay.n_levels;
+    for (int l = 0; l < lay.n_levels; ++l) {
+        T.size[l] = lay.size[l];
+        T.lvl[l] = (lay.in_smem[l] ? smem_d : ws_d) + lay.offset[l];
+    }
+}
+
+// Writes the node records of the new children, retires the expanded leaf from
+// the frontier and refreshes the tournament.  Called by warp 0 only.
+__device__ __forceinline__ void commit_expansion(const OpdArgs& a, Tournament& T, Shared& sh, int64_t nb, int leaf,
+                                                 int c0, int n, int it, int32_t* exp_order, int lane) {
+    const b2_opd_tree& tr = a.tree;
+    const int d = sh.depth + 1;
+    if (lane < n) {
+        const int c = c0 + lane;
+        const double r = sh.child_reward[lane];
+        const bool done = sh.child_done[lane] != 0;
+        // DeterministicNode.update (deterministic.py:52-63)
+        double lo = sh.lower + a.cfg.gamma_pow[d - 1] * r;
+        double up = lo + a.cfg.gamma_pow_div[d];
+        if (done) {
+            lo = lo + a.cfg.terminal_reward * a.cfg.gamma_pow_div[d];
+            up = lo;
+        }
+        tr.parent[nb + c] = leaf;
+        tr.first_child[nb + c] = -1;
+        tr.depth[nb + c] = d;
+        tr.count[nb + c] = 2;   // 1 at creation (:18) + 1 for its own update (:64-65)
+        tr.meta[nb + c] = sh.child_action[lane] | (done ? 1 << 16 : 0);
+        tr.reward[nb + c] = r;
+        tr.lower[nb + c] = lo;
+        tr.upper[nb + c] = up;
+        T.lvl[0][c] = up;
+        if (!(r >= 0.0 && r <= 1.0)) sh.error = 1;   // :46-47
+    }
+    if (lane == 0) {
+        T.lvl[0][leaf] = -INFINITY;
+        tr.first_child[nb + leaf] = c0;
+        tr.meta[nb + leaf] |= n << 8;
+        exp_order[it] = leaf;
+    }
+    __syncwarp();
+    T.update(leaf, lane);
+    T.update(c0, lane);
+    if (((c0 + n - 1) >> 5) != (c0 >> 5)) T.update(c0 + n - 1, lane);
+}
+
+// Bottom-up pass in reverse expansion order + greedy plan.  Warp 0 only.
+__device__ void finish_tree(const OpdArgs& a, int64_t nb, int tree_id, int n_nodes, int n_exp, int max_depth,
+                            int term_exp, int error, const int32_t* exp_order, int lane) {
+    const b2_opd_tree& tr = a.tree;
+    for (int k = n_exp - 1; k >= 0; --k) {
+        const int p = exp_order[k];
+        const int fc = tr.first_child[nb + p];
+        const int n = (tr.meta[nb + p] >> 8) & 0xff;
+        double lo = -INFINITY, up = -INFINITY;
+        int desc = 0;
+        if (lane < n) {
+            lo = tr.lower[nb + fc + lane];
+            up = tr.upper[nb + fc + lane];
+            desc = tr.count[nb + fc + lane] - 1;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {   // MAX_BRANCH = 8 lanes
+            const double lo2 = __shfl_xor_sync(0xffffffffu, lo, o);
+            const double up2 = __shfl_xor_sync(0xffffffffu, up, o);
+            lo = lo2 > lo ? lo2 : lo;
+            up = up2 > up ? up2 : up;
+            desc += __shfl_xor_sync(0xffffffffu, desc, o);
+        }
+        if (lane == 0) {
+            tr.lower[nb + p] = lo;       // backup_to_root (:74-79)
+            tr.upper[nb + p] = up;
+            tr.count[nb + p] = (p == 0 ? 1 : 2) + desc;
+        }
+        __syncwarp();
+    }
+    // get_plan (abstract.py:143-156) on value_lower; a tie needs the planner RNG
+    // (abstract.py:304-311): stop there and let the host finish the walk.
+    int8_t* plan = a.plan + (int64_t)tree_id * a.cfg.plan_capacity;
+    int node = 0, len = 0, tie_node = -1;
+    while (true) {
+        const int fc = tr.first_child[nb + node];
+        if (fc < 0) break;
+        const int n = (tr.meta[nb + node] >> 8) & 0xff;
+        double lo = lane < n ? tr.lower[nb + fc + lane] : -INFINITY;
+        const double m = warp_max_f64(lo);
+        const unsigned eq = __ballot_sync(0xffffffffu, lane < n && lo == m);
+        if (__popc(eq) > 1) { tie_node = node; break; }
+        const int c = fc + __ffs(eq) - 1;
+        if (lane == 0 && len < a.cfg.plan_capacity) plan[len] = (int8_t)(tr.meta[nb + c] & 0xff);
+        ++len;
+        node = c;
+    }
+    if (lane == 0) {
+        int32_t* res = a.result + (int64_t)tree_id * B2_OPD_RESULT_WORDS;
+        res[0] = n_nodes;
+        res[1] = n_nodes - n_exp;
+        res[2] = max_depth;
+        res[3] = term_exp;
+        res[4] = error;
+        res[5] = len;
+        res[6] = tie_node;
+    }
+}
+
+__device__ __forceinline__ void init_tree(const OpdArgs& a, Tournament& T, int64_t nb, int tid, int nthreads) {
+    for (int l = 0; l < T.n_levels; ++l)
+        for (int i = tid; i < T.size[l]; i += nthreads) T.lvl[l][i] = (i == 0) ? 0.0 : -INFINITY;
+    if (tid == 0) {   // DeterministicNode.__init__ (:10-19)
+        const b2_opd_tree& tr = a.tree;
+        tr.parent[nb] = -1;
+        tr.first_child[nb] = -1;
+        tr.depth[nb] = 0;
+        tr.count[nb] = 1;
+        tr.meta[nb] = 0xff;   // no action
+        tr.reward[nb] = 0.0;
+        tr.lower[nb] = 0.0;
+        tr.upper[nb] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// finite deterministic MDP: one warp per tree, lane a expands action a
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) opd_finite_kernel(OpdArgs a) {
+    extern __shared__ double smem_d[];
+    __shared__ Shared sh;
+    const int tree_id = blockIdx.x, lane = threadIdx.x;
+    const int64_t nb = (int64_t)tree_id * a.cfg.node_capacity;
+    char* ws = a.workspace + (int64_t)tree_id * a.lay.ws_bytes_per_tree;
+    Tournament T;
+    setup_tournament(T, a.lay, smem_d, (double*)ws);
+    int32_t* exp_order = (int32_t*)(ws + a.lay.ws_doubles * 8);
+    init_tree(a, T, nb, lane, 32);
+    if (lane == 0) {
+        a.tree.state[nb] = a.root_states[tree_id];
+        sh.error = 0;
+    }
+    __syncwarp();
+    const b2_finite_mdp& m = a.cfg.mdp;
+    const int A = a.cfg.n_actions;
+    int n_nodes = 1, max_depth = 0, term_exp = 0, it = 0;
+    for (; it < a.cfg.n_expansions; ++it) {
+        const int leaf = T.select(lane);
+        const int s = a.tree.state[nb + leaf];
+        if (lane == 0) {
+            sh.depth = a.tree.depth[nb + leaf];
+            sh.lower = a.tree.lower[nb + leaf];
+            sh.done_parent = (a.tree.meta[nb + leaf] >> 16) & 1;
+        }
+        if (lane < A) {   // deterministic.py:36-43 for action `lane`
+            const int s2 = m.transition[(int64_t)s * A + lane];
+            sh.child_reward[lane] = m.reward[(int64_t)s * A + lane];
+            sh.child_done[lane] = m.terminal[s2];
+            sh.child_action[lane] = lane;
+            a.tree.state[nb + n_nodes + lane] = s2;
+        }
+        __syncwarp();
+        term_exp += sh.done_parent;
+        max_depth = max(max_depth, sh.depth + 1);
+        commit_expansion(a, T, sh, nb, leaf, n_nodes, A, it, exp_order, lane);
+        n_nodes += A;
+        __syncwarp();
+        if (sh.error) { ++it; break; }
+    }
+    finish_tree(a, nb, tree_id, n_nodes, it, max_depth, term_exp, sh.error, exp_order, lane);
+}
+
+// ---------------------------------------------------------------------------
+// HighwayLite: 3 warps per tree; each 16-lane group simulates one child
+// ---------------------------------------------------------------------------
+constexpr int HW_THREADS = 96;
+
+__global__ void __launch_bounds__(HW_THREADS) opd_highway_kernel(OpdArgs a) {
+    extern __shared__ double smem_d[];
+    __shared__ Shared sh;
+    const int tree_id = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid >> 4, li = tid & 15;
+    const int64_t nb = (int64_t)tree_id * a.cfg.node_capacity;
+    char* ws = a.workspace + (int64_t)tree_id * a.lay.ws_bytes_per_tree;
+    Tournament T;
+    setup_tournament(T, a.lay, smem_d, (double*)ws);
+    int32_t* exp_order = (int32_t*)(ws + a.lay.ws_doubles * 8);
+    int32_t* states = a.tree.state + nb * hw::WORDS;
+    init_tree(a, T, nb, tid, HW_THREADS);
+    for (int i = tid; i < hw::WORDS; i += HW_THREADS) states[i] = a.root_states[(int64_t)tree_id * hw::WORDS + i];
+    if (tid == 0) sh.error = 0;
+    __syncthreads();
+    int n_nodes = 1, max_depth = 0, term_exp = 0, it = 0;
+    for (; it < a.cfg.n_expansions; ++it) {
+        if (warp == 0) {
+            const int leaf = T.select(lane);
+            if (lane == 0) {
+                sh.leaf = leaf;
+                sh.depth = a.tree.depth[nb + leaf];
+                sh.lower = a.tree.lower[nb + leaf];
+                sh.done_parent = (a.tree.meta[nb + leaf] >> 16) & 1;
+            }
+        }
+        __syncthreads();
+        const int leaf = sh.leaf;
+        // "deep copy" of the parent scene into registers (deterministic.py:38)
+        hw::Lane L;
+        int t, si;
+        hw::load_state(states + (int64_t)leaf * hw::WORDS, li, L, t, si);
+        const float ego_y = __shfl_sync(0xffffffffu, L.y, 0, 16);
+        const int mask = hw::avail_mask(ego_y, si);
+        const int n = __popc(mask);
+        const int action = grp < n ? hw::nth_action(mask, grp) : hw::A_IDLE;
+        bool term, trunc;
+        const float r = hw::step(L, li, t, si, action, term, trunc);
+        if (grp < n) {
+            hw::store_state(states + (int64_t)(n_nodes + grp) * hw::WORDS, li, L, t, si);
+            if (li == 0) {
+                sh.child_reward[grp] = (double)r;
+                sh.child_done[grp] = term ? 1 : 0;
+                sh.child_action[grp] = action;
+            }
+        }
+        __syncthreads();
+        term_exp += sh.done_parent;
+        max_depth = max(max_depth, sh.depth + 1);
+        if (warp == 0) commit_expansion(a, T, sh, nb, leaf, n_nodes, n, it, exp_order, lane);
+        n_nodes += n;
+        __syncthreads();
+        if (sh.error) { ++it; break; }
+    }
+    if (warp == 0) finish_tree(a, nb, tree_id, n_nodes, it, max_depth, term_exp, sh.error, exp_order, lane);
+}
+
+// ---------------------------------------------------------------------------
+// batched env transition (b2_highway_step): one scene per 16-lane group
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) highway_step_kernel(int32_t* states, const int32_t* actions, float* reward,
+                                                           int32_t* flags, int32_t* avail, int n_envs) {
+    const int g = (blockIdx.x * 128 + threadIdx.x) >> 4, li = threadIdx.x & 15;
+    const bool live = g < n_envs;
+    const int e = live ? g : n_envs - 1;
+    hw::Lane L;
+    int t, si;
+    hw::load_state(states + (int64_t)e * hw::WORDS, li, L, t, si);
+    bool term, trunc;
+    const float r = hw::step(L, li, t, si, actions[e], term, trunc);
+    const float ego_y = __shfl_sync(0xffffffffu, L.y, 0, 16);
+    if (live) {
+        hw::store_state(states + (int64_t)e * hw::WORDS, li, L, t, si);
+        if (li == 0) {
+            reward[e] = r;
+            flags[e] = (term ? 1 : 0) | (trunc ? 2 : 0);
+            if (avail) avail[e] = hw::avail_mask(ego_y, si);
+        }
+    }
+}
+
+static int make_layout(const b2_opd_config* cfg, LevelLayout* lay, int smem_budget_doubles) {
+    int n = cfg->node_capacity, l = 0;
+    lay->n_levels = 0;
+    while (true) {
+        if (l >= MAX_LEVELS) return -1;
+        lay->size[l] = n;
+        ++l;
+        if (n <= 32) break;
+        n = (n + 31) / 32;
+    }
+    lay->n_levels = l;
+    // upper levels are the hottest: place from the top down while they fit
+    int64_t smem_used = 0, ws_used = 0;
+    for (int k = l - 1; k >= 0; --k) {
+        const int64_t sz = (lay->size[k] + 1) & ~1;
+        const bool want = (k > 0) || cfg->keys_in_smem;
+        if (want && smem_used + sz <= smem_budget_doubles) {
+            lay->in_smem[k] = 1;
+            lay->offset[k] = smem_used;
+            smem_used += sz;
+        } else {
+            lay->in_smem[k] = 0;
+            lay->offset[k] = ws_used;
+            ws_used += sz;
+        }
+    }
+    lay->smem_doubles = (int)smem_used;
+    lay->ws_doubles = ws_used;
+    int64_t bytes = ws_used * 8 + (int64_t)cfg->n_expansions * 4;
+    lay->ws_bytes_per_tree = (bytes + 127) & ~(int64_t)127;
+    return 0;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+static const int kSmemBudgetDoubles = (96 * 1024) / 8;
+
+extern "C" int64_t b2_opd_workspace_bytes(const b2_opd_config* cfg) {
+    LevelLayout lay;
+    if (!cfg || make_layout(cfg, &lay, kSmemBudgetDoubles)) return -1;
+    return lay.ws_bytes_per_tree * (int64_t)cfg->n_trees;
+}
+
+extern "C" int b2_opd_plan(const b2_opd_config* cfg, const int32_t* root_states, const b2_opd_tree* tree,
+                           void* workspace, int8_t* plan, int32_t* result, void* stream_) {
+    B2_REQUIRE(cfg && root_states && tree && workspace && plan && result, "null pointer");
+    B2_REQUIRE(cfg->n_trees > 0 && cfg->n_expansions >= 0, "bad batch / budget");
+    B2_REQUIRE(cfg->n_actions > 0 && cfg->n_actions <= MAX_BRANCH, "n_actions must be in 1..8");
+    B2_REQUIRE((int64_t)cfg->node_capacity >= 1 + (int64_t)cfg->n_expansions * cfg->n_actions, "node_capacity too small");
+    B2_REQUIRE(cfg->plan_capacity >= cfg->n_expansions + 1, "plan_capacity too small");
+    B2_REQUIRE(cfg->gamma_pow && cfg->gamma_pow_div, "gamma tables missing");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    OpdArgs a;
+    a.cfg = *cfg; a.tree = *tree; a.root_states = root_states; a.workspace = (char*)workspace;
+    a.plan = plan; a.result = result;
+    if (make_layout(cfg, &a.lay, kSmemBudgetDoubles)) {
+        set_error("node_capacity %d exceeds 32^%d", cfg->node_capacity, MAX_LEVELS);
+        return B2_ERR_UNSUPPORTED;
+    }
+    const size_t smem = (size_t)a.lay.smem_doubles * 8;
+    if (cfg->env_kind == B2_ENV_FINITE) {
+        B2_REQUIRE(cfg->mdp.transition && cfg->mdp.reward && cfg->mdp.terminal, "finite MDP tables missing");
+        B2_REQUIRE(cfg->mdp.n_actions == cfg->n_actions, "mdp.n_actions != n_actions");
+        B2_CUDA_CHECK(cudaFuncSetAttribute(opd_finite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opd_finite_kernel<<<cfg->n_trees, 32, smem, stream>>>(a);
+    } else if (cfg->env_kind == B2_ENV_HIGHWAY) {
+        B2_REQUIRE(cfg->n_actions == B2_HW_ACTIONS, "HighwayLite has 5 actions");
+        B2_CUDA_CHECK(cudaFuncSetAttribute(opd_highway_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        opd_highway_kernel<<<cfg->n_trees, HW_THREADS, smem, stream>>>(a);
+    } else {
+        set_error("unknown env_kind %d", cfg->env_kind);
+        return B2_ERR_INVALID;
+    }
+    B2_CUDA_CHECK(cudaGetLastError());
+    return B2_OK;
+}
+
+extern "C" int b2_highway_step(int32_t* states, const int32_t* actions, float* reward, int32_t* flags,
+                               int32_t* avail_mask, int32_t n_envs, void* stream) {
+    B2_REQUIRE(states && actions && reward && flags && n_envs > 0, "null pointer / empty batch");
+    const int groups_per_block = 128 / 16;
+    const int grid = (n_envs + groups_per_block - 1) / groups_per_block;
+    highway_step_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(states, actions, reward, flags, avail_mask, n_envs);
+    B2_CUDA_CHECK(cudaGetLastError());
+    return B2_OK;
+}

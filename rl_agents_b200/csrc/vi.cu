@@ -1,0 +1,239 @@
+// Value-iteration Bellman sweep (value_iteration.py:51-73 of the reference).
+//
+// One launch = one application of  Q' = R + gamma * E[V(s')]  over a slab of
+// states, fused with V' = max_a Q' (best_action_value, :47-49) and with the
+// element-wise np.allclose(Q, Q') test of fixed_point_iteration (:70).
+//
+// HBM-bound: per (s,a,b) the kernel streams 8 B of P and 4 B of N
+// once, gathers 8 B of V (L2 resident: 8 MB at S=1e6), and per (s,a) streams
+// R, Q_old in and Q' out.  Summation order over the successor axis is numpy's
+// pairwise_sum so that results are bit-identical with the reference's
+// `(P * take(V, N)).sum(axis=-1)`.
+#include "common.cuh"
+
+namespace b2 {
+
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src):
+// < 8 sequential; <= 128 eight strided accumulators; else split in halves.
+template <typename Load>
+__device__ __noinline__ double np_pairwise_sum_big(Load a, int lo, int n) {
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = a(lo + j);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += a(lo + i + j);
+        }
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a(lo + i);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum_big(a, lo, n2) + np_pairwise_sum_big(a, lo + n2, n - n2);
+}
+
+template <typename Load>
+__device__ __forceinline__ double np_pairwise_sum(Load a, int lo, int n) {
+    if (n < 8) {   // the common sparse case (B = 2..4): stays inline, no call
+        double res = 0.;
+        for (int i = 0; i < n; ++i) res += a(lo + i);
+        return res;
+    }
+    return np_pairwise_sum_big(a, lo, n);
+}
+
+__device__ __forceinline__ bool np_isclose(double a, double b, double rtol, double atol) {
+    // numpy.isclose: finite -> |a-b| <= atol + rtol*|b| ; otherwise a == b
+    if (isfinite(a) && isfinite(b)) return fabs(a - b) <= atol + rtol * fabs(b);
+    return a == b;
+}
+
+struct SweepArgs {
+    const double* P;       // sparse/stochastic probabilities (slab-local)
+    const int32_t* N;      // sparse successors or deterministic transition
+    const double* R;
+    const uint8_t* term;
+    const double* v_in;
+    const double* q_old;
+    double* q_new;
+    double* v_out;
+    int32_t* viol;
+    int32_t sweep;
+    int64_t rows;          // states in the slab
+    int64_t row_begin;
+    int A, B;
+    int tile_states;
+    double gamma, rtol, atol;
+};
+
+// Sparse (B successors) and deterministic (B = 1, P == nullptr) modes.
+// CTA = tile of `tile_states` states; dynamic smem: prod[tile*A*B] + q[tile*A].
+__global__ void __launch_bounds__(256, 4) vi_sweep_gather_kernel(SweepArgs g) {
+    if (g.sweep > 0 && g.viol[g.sweep - 1] == 0) return;   // already converged
+    extern __shared__ double smem[];
+    const int E = g.A * g.B;
+    double* prod = smem;
+    double* qs = smem + (size_t)g.tile_states * E;
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (g.rows + g.tile_states - 1) / g.tile_states;
+    int bad = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t s0 = tile * g.tile_states;
+        const int ns = (int)min((int64_t)g.tile_states, g.rows - s0);
+        const int ne = ns * E;
+        const int64_t base = s0 * E;
+        // phase 1: stream P/N coalesced, gather V, stage products
+        if (g.P) {
+            constexpr int U = 4;
+            for (int i0 = tid; i0 < ne; i0 += 256 * U) {
+                double p[U];
+                int32_t n[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    int i = i0 + u * 256;
+                    if (i < ne) {
+                        p[u] = __ldcs(g.P + base + i);
+                        n[u] = __ldcs(g.N + base + i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    int i = i0 + u * 256;
+                    if (i < ne) prod[i] = p[u] * __ldg(g.v_in + n[u]);
+                }
+            }
+        } else {
+            for (int i = tid; i < ne; i += 256) prod[i] = __ldg(g.v_in + __ldcs(g.N + base + i));
+        }
+        __syncthreads();
+        // phase 2: one thread per (s,a): successor sum in numpy order, Bellman, allclose
+        const int nsa = ns * g.A;
+        for (int r = tid; r < nsa; r += 256) {
+            double nv = np_pairwise_sum([&](int i) { return prod[i]; }, r * g.B, g.B);
+            const int s = r / g.A;
+            if (g.term[s0 + s]) nv = 0.0;
+            const int64_t qi = s0 * g.A + r;
+            const double q = __ldcs(g.R + qi) + g.gamma * nv;
+            const double qo = __ldcs(g.q_old + qi);
+            if (!np_isclose(qo, q, g.rtol, g.atol)) bad++;
+            __stcs(g.q_new + qi, q);
+            qs[r] = q;
+        }
+        __syncthreads();
+        // phase 3: V' = max_a Q'
+        for (int s = tid; s < ns; s += 256) {
+            double m = qs[s * g.A];
+            for (int a = 1; a < g.A; ++a) {
+                double x = qs[s * g.A + a];
+                m = x > m ? x : m;
+            }
+            g.v_out[g.row_begin + s0 + s] = m;
+        }
+        __syncthreads();
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((tid & 31) == 0 && bad) atomicAdd(g.viol + g.sweep, bad);
+}
+
+// Dense stochastic mode: one thread per (s,a) row, numpy summation order.
+__global__ void __launch_bounds__(128) vi_sweep_dense_kernel(SweepArgs g) {
+    if (g.sweep > 0 && g.viol[g.sweep - 1] == 0) return;
+    extern __shared__ double smem[];   // q of the CTA's rows: [128]
+    const int tid = threadIdx.x;
+    const int64_t n_rows = g.rows * g.A;
+    // CTA covers 128 consecutive (s,a) rows; requires 128 % A == 0 or handles V by atomics-free pass below
+    const int64_t row = (int64_t)blockIdx.x * 128 + tid;
+    int bad = 0;
+    double q = 0.0;
+    if (row < n_rows) {
+        const double* p = g.P + row * (int64_t)g.B;
+        double nv = np_pairwise_sum([&](int i) { return p[i] * g.v_in[i]; }, 0, g.B);
+        const int64_t s = row / g.A;
+        if (g.term[s]) nv = 0.0;
+        q = g.R[row] + g.gamma * nv;
+        if (!np_isclose(g.q_old[row], q, g.rtol, g.atol)) bad = 1;
+        g.q_new[row] = q;
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((tid & 31) == 0 && bad) atomicAdd(g.viol + g.sweep, bad);
+}
+
+// V' = max_a Q' for the dense mode (rows may straddle CTAs there)
+__global__ void vi_rowmax_kernel(SweepArgs g) {
+    if (g.sweep > 0 && g.viol[g.sweep - 1] == 0) return;
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.rows) return;
+    const double* q = g.q_new + s * g.A;
+    double m = q[0];
+    for (int a = 1; a < g.A; ++a) m = q[a] > m ? q[a] : m;
+    g.v_out[g.row_begin + s] = m;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_vi_sweep(const b2_vi_problem* p, const double* v_in, const double* q_old, double* q_new,
+                           double* v_out, int32_t* viol, int32_t sweep_index, void* stream_) {
+    B2_REQUIRE(p && v_in && q_old && q_new && v_out && viol, "null pointer");
+    B2_REQUIRE(p->n_actions > 0 && p->row_end >= p->row_begin && p->row_end <= p->n_states, "bad shape");
+    B2_REQUIRE(sweep_index >= 0, "sweep_index < 0");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SweepArgs g;
+    g.R = p->reward; g.term = p->terminal; g.v_in = v_in; g.q_old = q_old; g.q_new = q_new; g.v_out = v_out;
+    g.viol = viol; g.sweep = sweep_index; g.rows = p->row_end - p->row_begin; g.row_begin = p->row_begin;
+    g.A = p->n_actions; g.gamma = p->gamma; g.rtol = p->rtol; g.atol = p->atol;
+    if (g.rows == 0) return B2_OK;
+    if (p->mode == B2_VI_STOCHASTIC) {
+        B2_REQUIRE(p->n_next == p->n_states, "stochastic mode: n_next must equal n_states");
+        g.P = (const double*)p->transition; g.N = nullptr; g.B = (int)p->n_states; g.tile_states = 0;
+        const int64_t n_rows = g.rows * g.A;
+        vi_sweep_dense_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, stream>>>(g);
+        vi_rowmax_kernel<<<(unsigned)((g.rows + 255) / 256), 256, 0, stream>>>(g);
+        B2_CUDA_CHECK(cudaGetLastError());
+        return B2_OK;
+    }
+    if (p->mode == B2_VI_SPARSE) {
+        B2_REQUIRE(p->n_next > 0 && p->next, "sparse mode needs next[] and n_next");
+        g.P = (const double*)p->transition; g.N = p->next; g.B = p->n_next;
+    } else if (p->mode == B2_VI_DETERMINISTIC) {
+        g.P = nullptr; g.N = (const int32_t*)p->transition; g.B = 1;
+    } else {
+        set_error("unknown VI mode %d", p->mode);
+        return B2_ERR_INVALID;
+    }
+    const int E = g.A * g.B;
+    B2_REQUIRE(E <= 8192, "n_actions * n_next > 8192 not supported by the tiled kernel");
+    int tile = 4096 / E;
+    if (tile < 1) tile = 1;
+    if (tile * g.A > 2048) tile = 2048 / g.A;
+    if (tile < 1) tile = 1;
+    g.tile_states = tile;
+    const size_t smem = ((size_t)tile * E + (size_t)tile * g.A) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2_CUDA_CHECK(cudaFuncSetAttribute(vi_sweep_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    const int64_t n_tiles = (g.rows + tile - 1) / tile;
+    const int64_t max_grid = (int64_t)sm_count() * 8;
+    const unsigned grid = (unsigned)(n_tiles < max_grid ? n_tiles : max_grid);
+    vi_sweep_gather_kernel<<<grid, 256, smem, stream>>>(g);
+    B2_CUDA_CHECK(cudaGetLastError());
+    return B2_OK;
+}
+
+extern "C" int b2_vi_solve(const b2_vi_problem* p, double* q0, double* q1, double* v0, double* v1,
+                           int32_t* viol, int32_t iterations, void* stream) {
+    B2_REQUIRE(p && p->row_begin == 0 && p->row_end == p->n_states, "b2_vi_solve needs the full state range");
+    double* q[2] = {q0, q1};
+    double* v[2] = {v0, v1};
+    for (int k = 0; k < iterations; ++k) {
+        int rc = b2_vi_sweep(p, v[k & 1], q[k & 1], q[(k + 1) & 1], v[(k + 1) & 1], viol, k, stream);
+        if (rc) return rc;
+    }
+    return B2_OK;
+}

@@ -1,0 +1,88 @@
+"""Batched MCTS engine (device side of MCTSAgent)."""
+import numpy as np
+
+from rl_agents_b200 import _lib
+from rl_agents_b200.engine.tables import FiniteTables, gamma_tables, uniform_cdf_table
+
+POLICIES = {"random_available": 0, "random": 1}
+
+
+def pcg64_words(gen):
+    """numpy Generator(PCG64) state -> the 6 x uint64 the kernel advances."""
+    st = gen.bit_generator.state
+    if st["bit_generator"] != "PCG64":
+        raise ValueError("the planner RNG must be a numpy PCG64 Generator")
+    s, inc = st["state"]["state"], st["state"]["inc"]
+    m = (1 << 64) - 1
+    return np.array([s >> 64, s & m, inc >> 64, inc & m, st["has_uint32"], st["uinteger"]], dtype=np.uint64)
+
+
+def set_pcg64_words(gen, w):
+    st = gen.bit_generator.state
+    w = [int(x) for x in w]
+    st["state"]["state"] = (w[0] << 64) | w[1]
+    st["state"]["inc"] = (w[2] << 64) | w[3]
+    st["has_uint32"], st["uinteger"] = w[4], w[5]
+    gen.bit_generator.state = st
+
+
+class MCTSEngine(object):
+    """n_trees independent MCTS decisions per launch; every tree consumes its
+    own numpy PCG64 stream exactly as the reference planner would."""
+
+    def __init__(self, env_kind, n_trees, n_actions, episodes, horizon, gamma, temperature, mdp=None,
+                 rollout_policy="random_available", prior_policy="random_available", device="cuda"):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        for pol in (rollout_policy, prior_policy):
+            if pol not in POLICIES:
+                raise ValueError("Unknown policy type")
+        self.n_trees, self.n_actions = int(n_trees), int(n_actions)
+        self.episodes, self.horizon = int(episodes), int(horizon)
+        self.capacity = 1 + self.episodes * self.n_actions
+        gp, _ = gamma_tables(gamma, self.horizon + 1)
+        self.gamma_pow = torch.as_tensor(gp, device=self.device)
+        self.cdf = torch.as_tensor(uniform_cdf_table(self.n_actions), device=self.device)
+        self.tables = FiniteTables(mdp, self.device) if env_kind == _lib.ENV_FINITE else None
+        shape = (self.n_trees, self.capacity)
+        i32, f64 = torch.int32, torch.float64
+        self.parent = torch.empty(shape, dtype=i32, device=self.device)
+        self.first_child = torch.empty(shape, dtype=i32, device=self.device)
+        self.count = torch.empty(shape, dtype=i32, device=self.device)
+        self.meta = torch.empty(shape, dtype=i32, device=self.device)
+        self.value = torch.empty(shape, dtype=f64, device=self.device)
+        self.prior = torch.empty(shape, dtype=f64, device=self.device)
+        self.cfg = _lib.MCTSConfig(env_kind, self.n_trees, self.n_actions, self.episodes, self.horizon, self.capacity,
+                                   POLICIES[rollout_policy], POLICIES[prior_policy], float(temperature),
+                                   self.gamma_pow.data_ptr(), self.cdf.data_ptr(),
+                                   self.tables.struct() if self.tables else _lib.FiniteMDP())
+        self.tree = _lib.MCTSTree(*[t.data_ptr() for t in (self.parent, self.first_child, self.count, self.meta,
+                                                           self.value, self.prior)])
+        self.plan_buf = torch.empty((self.n_trees, max(self.horizon, 1)), dtype=torch.int8, device=self.device)
+        self.result = torch.empty((self.n_trees, _lib.MCTS_RESULT_WORDS), dtype=i32, device=self.device)
+        self.rng = torch.empty((self.n_trees, _lib.PCG64_STATE_WORDS), dtype=torch.int64, device=self.device)
+
+    def plan(self, root_states, rng_words):
+        """rng_words: uint64 [n_trees, 6] numpy (pcg64_words per tree)."""
+        self.rng.copy_(self.torch.from_numpy(np.ascontiguousarray(rng_words).view(np.int64)))
+        _lib.check(self.lib.b2_mcts_plan(self.cfg, _lib.ptr(root_states), self.tree, _lib.ptr(self.rng),
+                                         _lib.ptr(self.plan_buf), _lib.ptr(self.result), _lib.current_stream()))
+
+    def finish(self):
+        """Synchronise; returns (plans, result array, advanced rng words)."""
+        res = self.result.cpu().numpy()
+        plans_dev = self.plan_buf.cpu().numpy()
+        plans = [plans_dev[i, :res[i, 1]].astype(int).tolist() for i in range(self.n_trees)]
+        return plans, res, self.rng.cpu().numpy().view(np.uint64)
+
+    def tree_dict(self, tree=0):
+        n = int(self.result[tree, 0].item())
+        meta = self.meta[tree, :n].cpu().numpy()
+        action = (meta & 0xff).astype(int)
+        action[action == 0xff] = -1
+        return {"parent": self.parent[tree, :n].cpu().numpy(), "action": action,
+                "count": self.count[tree, :n].cpu().numpy(), "value": self.value[tree, :n].cpu().numpy(),
+                "prior": self.prior[tree, :n].cpu().numpy(),
+                "first_child": self.first_child[tree, :n].cpu().numpy(), "n_children": (meta >> 8) & 0xff}

@@ -1,0 +1,41 @@
+"""Host-computed tables the kernels read so that their floating point matches
+the reference's Python float arithmetic bit for bit."""
+import numpy as np
+
+
+def gamma_tables(gamma, n):
+    """gamma**d and gamma**d/(1-gamma) with Python float `**` (deterministic.py:52-53)."""
+    gamma = float(gamma)
+    gp = np.array([gamma ** d for d in range(n)], dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        gd = np.array([(gamma ** d) / (1 - gamma) if gamma != 1 else np.inf for d in range(n)], dtype=np.float64)
+    return gp, gd
+
+
+def uniform_cdf_table(n_actions):
+    """Row n: cumsum(ones(n)/n)/cumsum[-1] -- the cdf Generator.choice(a, 1, p=p)
+    searches for a uniform p over n actions (mcts.py:60-72,172)."""
+    t = np.ones((n_actions + 1, n_actions), dtype=np.float64)
+    for n in range(1, n_actions + 1):
+        cdf = (np.ones(n) / n).cumsum()
+        cdf /= cdf[-1]
+        t[n, :n] = cdf
+    return t
+
+
+class FiniteTables(object):
+    """Device copy of a deterministic finite MDP (int32 transitions)."""
+
+    def __init__(self, mdp, device):
+        import torch
+        if mdp.mode != "deterministic":
+            raise ValueError("tree search on a finite MDP needs mode == 'deterministic' (got %r)" % mdp.mode)
+        self.n_states, self.n_actions = mdp.reward.shape
+        self.transition = torch.as_tensor(np.ascontiguousarray(mdp.transition, dtype=np.int32), device=device)
+        self.reward = torch.as_tensor(np.ascontiguousarray(mdp.reward, dtype=np.float64), device=device)
+        self.terminal = torch.as_tensor(np.ascontiguousarray(mdp.terminal, dtype=np.uint8), device=device)
+
+    def struct(self):
+        from rl_agents_b200 import _lib
+        return _lib.FiniteMDP(self.n_states, self.n_actions, self.transition.data_ptr(),
+                              self.reward.data_ptr(), self.terminal.data_ptr())

@@ -1,0 +1,83 @@
+"""Value-iteration engine (device side of ValueIterationAgent)."""
+import numpy as np
+
+from rl_agents_b200 import _lib
+
+MODES = {"deterministic": _lib.VI_DETERMINISTIC, "stochastic": _lib.VI_STOCHASTIC, "sparse": _lib.VI_SPARSE}
+
+
+class VIEngine(object):
+    """Holds the slab [row_begin, row_end) of an MDP's tables on one device and
+    runs Bellman sweeps (b2_vi_sweep).  With world_size > 1 every rank owns a
+    slab and V is all-gathered after each sweep (rl_agents_b200.distributed)."""
+
+    def __init__(self, mode, transition, reward, terminal, nxt=None, gamma=1.0, device="cuda",
+                 row_begin=0, row_end=None, n_states=None, rtol=1e-5, atol=1e-8):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.mode = mode
+        reward = np.asarray(reward, dtype=np.float64)
+        rows, A = reward.shape
+        self.n_actions = A
+        self.n_states = int(n_states if n_states is not None else rows)
+        self.row_begin = int(row_begin)
+        self.row_end = int(row_end if row_end is not None else self.row_begin + rows)
+        assert self.row_end - self.row_begin == rows
+        if mode == "deterministic":
+            self.transition = torch.as_tensor(np.ascontiguousarray(transition, dtype=np.int32), device=self.device)
+            self.next, self.n_next = None, 1
+        elif mode == "stochastic":
+            self.transition = torch.as_tensor(np.ascontiguousarray(transition, dtype=np.float64), device=self.device)
+            self.next, self.n_next = None, self.n_states
+        elif mode == "sparse":
+            self.transition = torch.as_tensor(np.ascontiguousarray(transition, dtype=np.float64), device=self.device)
+            self.next = torch.as_tensor(np.ascontiguousarray(nxt, dtype=np.int32), device=self.device)
+            self.n_next = int(self.next.shape[-1])
+        else:
+            raise ValueError("Unknown mode")
+        self.reward = torch.as_tensor(np.ascontiguousarray(reward), device=self.device)
+        self.terminal = torch.as_tensor(np.ascontiguousarray(terminal, dtype=np.uint8), device=self.device)
+        self.problem = _lib.VIProblem(MODES[mode], A, self.n_next, 0, self.n_states, self.row_begin, self.row_end,
+                                      float(gamma), rtol, atol, self.transition.data_ptr(),
+                                      self.next.data_ptr() if self.next is not None else None,
+                                      self.reward.data_ptr(), self.terminal.data_ptr())
+        self.q = [torch.zeros(rows, A, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.v = [torch.zeros(self.n_states, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.viol = None
+
+    def bytes_per_sweep(self):
+        """Algorithmic HBM bytes of one sweep (SURVEY 8d formula, + the Q_old read)."""
+        rows, A, B = self.row_end - self.row_begin, self.n_actions, self.n_next
+        if self.mode == "deterministic":
+            return rows * A * (4 + 8 + 8 + 8 + 8) + rows * 9
+        return rows * A * B * (8 + (4 if self.mode == "sparse" else 0) + 8) + rows * A * (8 + 8 + 8) + rows * 9
+
+    def reset(self, iterations):
+        for t in self.q + self.v:
+            t.zero_()
+        self.viol = self.torch.zeros(max(int(iterations), 1), dtype=self.torch.int32, device=self.device)
+
+    def sweep(self, k):
+        """Enqueue sweep k: reads q[k%2], v[k%2]; writes q[(k+1)%2], v[(k+1)%2]."""
+        _lib.check(self.lib.b2_vi_sweep(self.problem, _lib.ptr(self.v[k & 1]), _lib.ptr(self.q[k & 1]),
+                                        _lib.ptr(self.q[(k + 1) & 1]), _lib.ptr(self.v[(k + 1) & 1]),
+                                        _lib.ptr(self.viol), k, _lib.current_stream()))
+
+    def solve(self, iterations):
+        """fixed_point_iteration (value_iteration.py:65-73) without host round trips;
+        returns (Q tensor on device, sweeps performed)."""
+        self.reset(iterations)
+        _lib.check(self.lib.b2_vi_solve(self.problem, _lib.ptr(self.q[0]), _lib.ptr(self.q[1]), _lib.ptr(self.v[0]),
+                                        _lib.ptr(self.v[1]), _lib.ptr(self.viol), int(iterations),
+                                        _lib.current_stream()))
+        return self.result(iterations)
+
+    def result(self, iterations):
+        viol = self.viol[:iterations].cpu().numpy()     # synchronises
+        zero = np.nonzero(viol == 0)[0]
+        if zero.size:                                    # converged at sweep k: return the OLD iterate
+            k = int(zero[0])
+            return self.q[k & 1], k + 1
+        return self.q[iterations & 1], int(iterations)

@@ -1,0 +1,308 @@
+"""GPU parity tests: the CUDA engines (through the C ABI) against the oracle and
+the golden vectors made by the unmodified reference.  Bit-exact: node order,
+counts, fp64 bounds / values, fp32 env states."""
+import numpy as np
+import pytest
+
+from oracle import envs as oenvs
+from oracle import planners
+from tests.util import assert_tree_matches, load_golden, load_mdps
+
+pytestmark = pytest.mark.gpu
+
+G = load_golden("golden_finite.json")
+H = load_golden("golden_highway.json")
+M = load_mdps()
+
+
+def np_random(seed):
+    return np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+
+
+def product_mdp(name="large1", terminal=None):
+    from rl_agents_b200.envs.finite_mdp import FiniteMDP
+    term = M[name + "_term"] if terminal is None else terminal
+    return FiniteMDP("deterministic", M[name + "_T"], M[name + "_R"], term)
+
+
+def terminal_variant():
+    term = M["large1_term"].copy()
+    term[[3, 17, 66, 91]] = True
+    return term
+
+
+# ------------------------------------------------------------------ env ----
+def test_highway_step_matches_golden_traces():
+    import torch
+    from rl_agents_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    for seed, steps in H["traces"].items():
+        st = torch.tensor(H["states"][seed] if seed in H["states"] else oenvs.make_highway_state(int(seed)).pack(),
+                          dtype=torch.int32, device=dev).reshape(1, -1).contiguous()
+        rew = torch.empty(1, dtype=torch.float32, device=dev)
+        flg = torch.empty(1, dtype=torch.int32, device=dev)
+        avail = torch.empty(1, dtype=torch.int32, device=dev)
+        for k, s in enumerate(steps):
+            act = torch.tensor([s["a"]], dtype=torch.int32, device=dev)
+            _lib.check(lib.b2_highway_step(_lib.ptr(st), _lib.ptr(act), _lib.ptr(rew), _lib.ptr(flg), _lib.ptr(avail), 1,
+                                           _lib.current_stream()))
+            assert st.cpu().numpy().reshape(-1).tolist() == s["state"], (seed, k)
+            assert float(rew.item()) == np.float32(s["r"])
+            assert int(flg.item()) == (1 if s["term"] else 0) | (2 if s["trunc"] else 0)
+            if k + 1 < len(steps):
+                mask = int(avail.item())
+                assert sorted(a for a in range(5) if mask >> a & 1) == sorted(steps[k + 1]["avail"])
+
+
+def test_highway_step_batched_vs_oracle_random():
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.envs.highway_lite import make_scene
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    n = 37   # odd: exercises the idle half-warp
+    scenes = [oenvs.HighwayLite(seed=100 + i) for i in range(n)]
+    for i in range(n):   # product and oracle scene generators agree
+        assert make_scene(100 + i).tolist() == scenes[i].state.pack().tolist()
+    st = torch.tensor(np.stack([e.state.pack() for e in scenes]), dtype=torch.int32, device=dev)
+    rng = np.random.default_rng(0)
+    rew = torch.empty(n, dtype=torch.float32, device=dev)
+    flg = torch.empty(n, dtype=torch.int32, device=dev)
+    for step in range(6):
+        acts = []
+        for e in scenes:
+            av = e.get_available_actions()
+            acts.append(int(av[rng.integers(len(av))]))
+        act = torch.tensor(acts, dtype=torch.int32, device=dev)
+        _lib.check(lib.b2_highway_step(_lib.ptr(st), _lib.ptr(act), _lib.ptr(rew), _lib.ptr(flg), None, n,
+                                       _lib.current_stream()))
+        got = st.cpu().numpy()
+        for i, e in enumerate(scenes):
+            _, r, term, trunc, _ = e.step(acts[i])
+            assert got[i].tolist() == e.state.pack().tolist(), (step, i)
+            assert float(rew[i].item()) == np.float32(r)
+            assert int(flg[i].item()) == (1 if term else 0) | (2 if trunc else 0)
+
+
+# ------------------------------------------------------------------- VI ----
+def vi_cases():
+    rng = np.random.default_rng(0)
+    P = rng.uniform(size=(100, 4, 100))
+    P /= P.sum(-1, keepdims=True)
+    R = rng.uniform(size=(100, 4))
+    Ps, Ns, Rs = oenvs.garnet(500, 4, 3, seed=1)
+    term = np.zeros(500, bool)
+    term[::37] = True
+    return {
+        "large1_g0.9_it100": ("deterministic", M["large1_T"], M["large1_R"], M["large1_term"], None),
+        "large1_g1.0_it2": ("deterministic", M["large1_T"], M["large1_R"], M["large1_term"], None),
+        "trap_g0.9_it100": ("deterministic", M["trap_T"], M["trap_R"], M["trap_term"], None),
+        "loop_g0.9_it100": ("deterministic", M["loop_T"], M["loop_R"], M["loop_term"], None),
+        "dense_c1_g0.95_it100": ("stochastic", P, R, np.zeros(100, bool), None),
+        "sparse_garnet500_g0.95_it100": ("sparse", Ps, Rs, term, Ns),
+    }
+
+
+@pytest.mark.parametrize("key", sorted(vi_cases()))
+def test_vi_golden(key):
+    from rl_agents_b200.engine.vi import VIEngine
+    mode, T, R, term, N = vi_cases()[key]
+    g = G["vi"][key]
+    eng = VIEngine(mode, T, R, term, nxt=N, gamma=g["gamma"])
+    q, sweeps = eng.solve(g["iterations"])
+    assert np.array_equal(q.cpu().numpy(), np.array(g["q"])), key
+    _, ref_sweeps = planners.value_iteration(mode, T if mode != "deterministic" else np.asarray(T), R,
+                                             term.astype(bool), g["gamma"], g["iterations"], nxt=N)
+    assert sweeps == ref_sweeps
+
+
+@pytest.mark.parametrize("S,A,B,seed", [(1000, 8, 1, 0), (777, 3, 2, 1), (5000, 8, 4, 2), (300, 5, 7, 3),
+                                        (257, 2, 8, 4), (200, 4, 19, 5), (64, 3, 130, 6), (1, 1, 1, 7)])
+def test_vi_sparse_random_vs_oracle(S, A, B, seed):
+    from rl_agents_b200.engine.vi import VIEngine
+    P, N, R = oenvs.garnet(S, A, B, seed=seed)
+    term = np.random.default_rng(seed).uniform(size=S) < 0.05
+    q_ref, sweeps_ref = planners.value_iteration("sparse", P, R, term, 0.93, 60, nxt=N)
+    eng = VIEngine("sparse", P, R, term, nxt=N, gamma=0.93)
+    q, sweeps = eng.solve(60)
+    assert sweeps == sweeps_ref
+    assert np.array_equal(q.cpu().numpy(), q_ref)
+
+
+def test_vi_early_exit_returns_previous_iterate():
+    from rl_agents_b200.engine.vi import VIEngine
+    T, R = oenvs.garnet(400, 4, 1, seed=9, deterministic=True)
+    term = np.zeros(400, bool)
+    q_ref, sweeps_ref = planners.value_iteration("deterministic", T, R, term, 0.5, 100)
+    assert sweeps_ref < 100     # converges early at gamma = 0.5
+    eng = VIEngine("deterministic", T, R, term, gamma=0.5)
+    q, sweeps = eng.solve(100)
+    assert sweeps == sweeps_ref
+    assert np.array_equal(q.cpu().numpy(), q_ref)
+
+
+def test_vi_slabs_compose():
+    """Two row slabs sharing V reproduce the single-slab sweep (the multi-GPU partition)."""
+    import torch
+    from rl_agents_b200.engine.vi import VIEngine
+    S, A, B = 1001, 4, 3
+    P, N, R = oenvs.garnet(S, A, B, seed=11)
+    term = np.zeros(S, bool)
+    full = VIEngine("sparse", P, R, term, nxt=N, gamma=0.9)
+    q_full, _ = full.solve(7)
+    cut = 400
+    slabs = [VIEngine("sparse", P[:cut], R[:cut], term[:cut], nxt=N[:cut], gamma=0.9, row_begin=0, n_states=S),
+             VIEngine("sparse", P[cut:], R[cut:], term[cut:], nxt=N[cut:], gamma=0.9, row_begin=cut, n_states=S)]
+    for e in slabs:
+        e.reset(7)
+    for k in range(7):
+        for e in slabs:
+            e.sweep(k)
+        torch.cuda.synchronize()
+        v = slabs[0].v[(k + 1) & 1]
+        v[cut:] = slabs[1].v[(k + 1) & 1][cut:]          # the all-gather step
+        slabs[1].v[(k + 1) & 1].copy_(v)
+        viol = slabs[0].viol + slabs[1].viol              # the all-reduce step
+        slabs[0].viol.copy_(viol)
+        slabs[1].viol.copy_(viol)
+    q = torch.cat([slabs[0].q[7 & 1], slabs[1].q[7 & 1]]).cpu().numpy()
+    assert np.array_equal(q, q_full.cpu().numpy())
+
+
+# ------------------------------------------------------------------ OPD ----
+def run_opd_finite(mdp, budget, gamma, roots, terminal_reward=0.0, keys_in_smem=False):
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDEngine
+    eng = OPDEngine(_lib.ENV_FINITE, len(roots), mdp.reward.shape[1], budget, gamma, terminal_reward, mdp=mdp,
+                    keys_in_smem=keys_in_smem)
+    eng.plan(torch.tensor(roots, dtype=torch.int32, device="cuda"))
+    plans, res = eng.finish([np_random(0) for _ in roots])
+    return eng, plans, res
+
+
+@pytest.mark.parametrize("key,mdp,smem", [("large1_b500_g0.9", "large1", False), ("large1_b500_g0.9", "large1", True),
+                                          ("large1_b75_g0.7", "large1", False),
+                                          ("large1_b10000_g0.9", "large1", False),
+                                          ("large1_b10000_g0.9", "large1", True),
+                                          ("large2_b2000_g0.8", "large2", False)])
+def test_opd_finite_golden(key, mdp, smem):
+    g = G["opd"][key]
+    eng, plans, res = run_opd_finite(product_mdp(mdp), g["budget"], g["gamma"], [0], keys_in_smem=smem)
+    assert plans[0] == g["plan"]
+    assert res[0, 1] == g["n_leaves"]
+    assert_tree_matches(eng.tree_dict(0), g["tree"], ["reward", "lower", "upper"])
+
+
+def test_opd_finite_terminal_golden():
+    g = G["opd"]["large1_terminal_b300_g0.85"]
+    eng, plans, res = run_opd_finite(product_mdp(terminal=terminal_variant()), 300, 0.85, [0])
+    assert plans[0] == g["plan"]
+    assert_tree_matches(eng.tree_dict(0), g["tree"], ["reward", "lower", "upper"])
+
+
+def test_opd_finite_batch_vs_oracle():
+    roots = [0, 5, 17, 42, 99, 63, 7]
+    term = terminal_variant()
+    eng, plans, res = run_opd_finite(product_mdp(terminal=term), 400, 0.8, roots, terminal_reward=0.25)
+    for i, s0 in enumerate(roots):
+        env = oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], term, state=s0)
+        plan, t = planners.opd_plan(env, 400, 0.8, terminal_reward=0.25, np_random=np_random(0))
+        d = eng.tree_dict(i)
+        assert plans[i] == plan
+        assert d["parent"].tolist() == t.parent and d["count"].tolist() == t.count
+        assert d["action"].tolist() == t.action
+        assert np.array_equal(d["lower"], np.array(t.lower)) and np.array_equal(d["upper"], np.array(t.upper))
+        assert res[i, 3] == t.terminal_expansions
+
+
+def test_opd_reward_out_of_range_raises():
+    with pytest.raises(ValueError):
+        run_opd_finite(product_mdp("trap"), 40, 0.9, [0])     # trap has reward -1
+
+
+def run_opd_highway(words_list, budget, gamma, keys_in_smem=False):
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDEngine
+    eng = OPDEngine(_lib.ENV_HIGHWAY, len(words_list), 5, budget, gamma, keys_in_smem=keys_in_smem)
+    eng.plan(torch.tensor(np.stack(words_list), dtype=torch.int32, device="cuda"))
+    plans, res = eng.finish([np_random(0) for _ in words_list])
+    return eng, plans, res
+
+
+@pytest.mark.parametrize("key,smem", [("s0_b75_g0.7", False), ("s1_b300_g0.8", False), ("s1_b300_g0.8", True),
+                                      ("s2_b1000_g0.8", False)])
+def test_opd_highway_golden(key, smem):
+    g = H["opd"][key]
+    words = np.array(H["states"][key[1]], dtype=np.int32)
+    eng, plans, res = run_opd_highway([words], g["budget"], g["gamma"], keys_in_smem=smem)
+    assert plans[0] == g["plan"]
+    assert_tree_matches(eng.tree_dict(0), g["tree"], ["reward", "lower", "upper"])
+
+
+def test_opd_highway_batch_vs_oracle():
+    seeds = [10, 11, 12]
+    words = [oenvs.make_highway_state(s).pack() for s in seeds]
+    eng, plans, res = run_opd_highway(words, 120, 0.75)
+    for i, s in enumerate(seeds):
+        plan, t = planners.opd_plan(oenvs.HighwayLite(seed=s), 120, 0.75, np_random=np_random(0))
+        d = eng.tree_dict(i)
+        assert plans[i] == plan
+        assert d["parent"].tolist() == t.parent and d["count"].tolist() == t.count and d["action"].tolist() == t.action
+        assert np.array_equal(d["lower"], np.array(t.lower)) and np.array_equal(d["upper"], np.array(t.upper))
+
+
+# ----------------------------------------------------------------- MCTS ----
+def run_mcts(env_kind, roots, episodes, horizon, gamma, temperature, seeds, mdp=None):
+    import torch
+    from rl_agents_b200.engine.mcts import MCTSEngine, pcg64_words
+    eng = MCTSEngine(env_kind, len(roots), 5, episodes, horizon, gamma, temperature, mdp=mdp)
+    gens = [np_random(s) for s in seeds]
+    eng.plan(torch.tensor(np.stack(roots), dtype=torch.int32, device="cuda").contiguous(),
+             np.stack([pcg64_words(g) for g in gens]))
+    plans, res, rng_words = eng.finish()
+    return eng, plans, res, rng_words, gens
+
+
+@pytest.mark.parametrize("key", sorted(G["mcts"]))
+def test_mcts_finite_golden(key):
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.mcts import pcg64_words
+    g = G["mcts"][key]
+    mdp = product_mdp(terminal=terminal_variant() if "terminal" in key else None)
+    eng, plans, res, rng_words, gens = run_mcts(_lib.ENV_FINITE, [np.int32(0)], g["episodes"], g["horizon"],
+                                                g["config"]["gamma"], g["temperature"], [g["seed"]], mdp=mdp)
+    assert plans[0] == g["plan"]
+    assert_tree_matches(eng.tree_dict(0), g["tree"], ["value", "prior"])
+    # the device consumed the stream exactly like the oracle (= the reference) does
+    term = terminal_variant() if "terminal" in key else M["large1_term"]
+    ref_rng = np_random(g["seed"])
+    planners.mcts_plan(oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], term), g["episodes"], g["horizon"],
+                       g["config"]["gamma"], g["temperature"], ref_rng)
+    assert rng_words[0].tolist() == pcg64_words(ref_rng).tolist()
+
+
+@pytest.mark.parametrize("key", sorted(H["mcts"]))
+def test_mcts_highway_golden(key):
+    from rl_agents_b200 import _lib
+    g = H["mcts"][key]
+    words = np.array(H["states"][key[1]], dtype=np.int32)
+    eng, plans, res, _, _ = run_mcts(_lib.ENV_HIGHWAY, [words], g["episodes"], g["horizon"], g["config"]["gamma"],
+                                     g["temperature"], [g["seed"]])
+    assert plans[0] == g["plan"]
+    assert_tree_matches(eng.tree_dict(0), g["tree"], ["value", "prior"])
+
+
+def test_mcts_highway_batch_vs_oracle():
+    from rl_agents_b200 import _lib
+    seeds = [20, 21, 22]   # odd batch: one idle half-warp
+    words = [oenvs.make_highway_state(s).pack() for s in seeds]
+    eng, plans, res, _, _ = run_mcts(_lib.ENV_HIGHWAY, words, 40, 5, 0.85, 10.0, [1, 2, 3])
+    for i, s in enumerate(seeds):
+        plan, t = planners.mcts_plan(oenvs.HighwayLite(seed=s), 40, 5, 0.85, 10.0, np_random(i + 1))
+        d = eng.tree_dict(i)
+        assert plans[i] == plan
+        assert d["parent"].tolist() == t.parent and d["count"].tolist() == t.count and d["action"].tolist() == t.action
+        assert np.array_equal(d["value"], np.array(t.value))
