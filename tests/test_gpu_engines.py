@@ -218,8 +218,16 @@ def test_opd_finite_batch_vs_oracle():
 
 
 def test_opd_reward_out_of_range_raises():
-    with pytest.raises(ValueError):
-        run_opd_finite(product_mdp("trap"), 40, 0.9, [0])     # trap has reward -1
+    from rl_agents_b200.envs.finite_mdp import FiniteMDP
+    for bad in (-0.5, 1.5):
+        R = M["large1_R"].copy()
+        R[24, 2] = bad           # state 24 = T[0,0]: reached at the second expansion
+        mdp = FiniteMDP("deterministic", M["large1_T"], R, M["large1_term"])
+        with pytest.raises(ValueError):      # deterministic.py:46-47
+            run_opd_finite(mdp, 500, 0.9, [0])
+        env = oenvs.FiniteMDPLite(M["large1_T"], R, M["large1_term"])
+        with pytest.raises(ValueError):
+            planners.opd_plan(env, 500, 0.9, np_random=np_random(0))
 
 
 def run_opd_highway(words_list, budget, gamma, keys_in_smem=False):
