@@ -191,6 +191,44 @@ typedef struct b2_mcts_tree {
 int b2_mcts_plan(const b2_mcts_config* cfg, const int32_t* root_states, const b2_mcts_tree* tree,
                  uint64_t* rng, int8_t* plan, int32_t* result, void* stream);
 
+/* ------------------------------------------------------------------------
+ * OLOP / KL-OLOP -- rl_agents/agents/tree_search/olop.py
+ * ---------------------------------------------------------------------- */
+typedef struct b2_olop_config {
+    int32_t env_kind;
+    int32_t n_trees;
+    int32_t n_actions;
+    int32_t episodes;        /* config["episodes"] (OLOP.allocation, :50-62)  */
+    int32_t horizon;         /* config["horizon"]                            */
+    int32_t node_capacity;   /* per tree, >= 1 + episodes*horizon*n_actions   */
+    int32_t kl;              /* 1: upper_bound.type == "kullback-leibler"; 0: the
+                                reference leaves mu_ucb = inf (:153-163)      */
+    int32_t continuation;    /* 0 "zeros", 1 "uniform" (:79-82)               */
+    double gamma;
+    const double* thresholds;/* [episodes] eval(upper_bound.threshold) per episode (:160) */
+    const double* init_upper;/* [horizon+2] (1 - gamma**(L+1-d)) / (1 - gamma) (:118-119) */
+    b2_finite_mdp mdp;
+} b2_olop_config;
+
+typedef struct b2_olop_tree {
+    int32_t* parent;
+    int32_t* first_child;
+    int32_t* count;
+    int32_t* meta;           /* action | n_children << 8 | done << 16          */
+    double* cumulative;      /* OLOPNode.cumulative_reward                     */
+    double* mu_ucb;
+    double* upper;           /* value_upper                                    */
+} b2_olop_tree;
+
+#define B2_OLOP_RESULT_WORDS 8
+/* per tree int32 result: [0] n_nodes [1] plan_len
+ * [2] error (1: reward outside [0,1], olop.py:133-134; 2: "zeros" continuation
+ *     with action 0 unavailable -- a KeyError in the reference, :82,:88) */
+
+/* OLOP.plan (:94-100); rng as in b2_mcts_plan; plan: int8 [n_trees, horizon]. */
+int b2_olop_plan(const b2_olop_config* cfg, const int32_t* root_states, const b2_olop_tree* tree,
+                 uint64_t* rng, int8_t* plan, int32_t* result, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ ENV_FINITE, ENV_HIGHWAY = 0, 1
 VI_DETERMINISTIC, VI_STOCHASTIC, VI_SPARSE = 0, 1, 2
 OPD_RESULT_WORDS = 16
 MCTS_RESULT_WORDS = 8
+OLOP_RESULT_WORDS = 8
 PCG64_STATE_WORDS = 6
 
 
@@ -56,6 +57,16 @@ class MCTSTree(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("parent", "first_child", "count", "meta", "value", "prior")]
 
 
+class OLOPConfig(ctypes.Structure):
+    _fields_ = [("env_kind", c_int32), ("n_trees", c_int32), ("n_actions", c_int32), ("episodes", c_int32),
+                ("horizon", c_int32), ("node_capacity", c_int32), ("kl", c_int32), ("continuation", c_int32),
+                ("gamma", c_double), ("thresholds", c_void_p), ("init_upper", c_void_p), ("mdp", FiniteMDP)]
+
+
+class OLOPTree(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("parent", "first_child", "count", "meta", "cumulative", "mu_ucb", "upper")]
+
+
 EXPORTS = {
     "b2_last_error": (ctypes.c_char_p, []),
     "b2_version": (c_int, []),
@@ -67,6 +78,8 @@ EXPORTS = {
     "b2_opd_plan": (c_int, [ctypes.POINTER(OPDConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
                             c_void_p, c_void_p]),
     "b2_mcts_plan": (c_int, [ctypes.POINTER(MCTSConfig), c_void_p, ctypes.POINTER(MCTSTree), c_void_p, c_void_p,
+                             c_void_p, c_void_p]),
+    "b2_olop_plan": (c_int, [ctypes.POINTER(OLOPConfig), c_void_p, ctypes.POINTER(OLOPTree), c_void_p, c_void_p,
                              c_void_p, c_void_p]),
 }
 

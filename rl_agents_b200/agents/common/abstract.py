@@ -15,6 +15,7 @@ class AbstractAgent(Configurable, ABC):
         super(AbstractAgent, self).__init__(config)
         self.writer = None
         self.directory = None
+        register_with_reference(type(self))
 
     @abstractmethod
     def record(self, state, action, reward, next_state, done, info):
@@ -58,9 +59,14 @@ class AbstractAgent(Configurable, ABC):
 
 def register_with_reference(cls):
     """isinstance(agent, rl_agents...AbstractAgent) holds when the reference is installed."""
+    import sys
+    ref = sys.modules.get("rl_agents.agents.common.abstract")
+    if ref is None and "rl_agents" not in sys.modules:
+        return cls          # reference not loaded in this process: nothing to register with
     try:
-        from rl_agents.agents.common.abstract import AbstractAgent as RefAgent
-        RefAgent.register(cls)
+        if ref is None:
+            from rl_agents.agents.common import abstract as ref
+        ref.AbstractAgent.register(cls)
     except Exception:
         pass
     return cls

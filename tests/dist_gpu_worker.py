@@ -1,0 +1,62 @@
+"""torchrun worker for tests/test_gpu_multi.py (one rank per GPU, NCCL)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from oracle import envs as oenvs
+    from oracle import planners
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.distributed import DistributedVI, merge_root_statistics, recommend, shard_range
+    from rl_agents_b200.engine.mcts import MCTSEngine, pcg64_words
+    out = {}
+    # --- slab-sharded VI vs the single-process oracle ---
+    S, A, B = 3001, 4, 3
+    P, N, R = oenvs.garnet(S, A, B, seed=5)
+    term = np.zeros(S, bool)
+    term[::101] = True
+    dvi = DistributedVI("sparse", P, R, term, nxt=N, gamma=0.6, device=dev)
+    q, sweeps = dvi.solve(80)
+    q_ref, sweeps_ref = planners.value_iteration("sparse", P, R, term, 0.6, 80, nxt=N)
+    b, e = shard_range(S, rank, world)
+    out["vi_ok"] = bool(np.array_equal(q.cpu().numpy(), q_ref[b:e])) and sweeps == sweeps_ref
+    out["vi_sweeps"] = sweeps
+    # --- root-parallel MCTS: one all-reduce of root statistics ---
+    words = oenvs.make_highway_state(3).pack()
+    ss = np.random.SeedSequence(11).spawn(world)[rank]
+    gen = np.random.Generator(np.random.PCG64(ss))
+    eng = MCTSEngine(_lib.ENV_HIGHWAY, 1, 5, 64 // world, 6, 0.8, 10.0, device=dev)
+    eng.plan(torch.tensor(words, dtype=torch.int32, device=dev).reshape(1, -1), pcg64_words(gen).reshape(1, -1))
+    eng.finish()
+    d = eng.tree_dict(0)
+    n = int(d["n_children"][0])
+    counts = torch.zeros(5, dtype=torch.int32, device=dev)
+    values = torch.zeros(5, dtype=torch.float64, device=dev)
+    for c in range(d["first_child"][0], d["first_child"][0] + n):
+        counts[d["action"][c]] = int(d["count"][c])
+        values[d["action"][c]] = float(d["value"][c])
+    mc, mv = merge_root_statistics(counts, values)
+    out["mcts_total"] = float(mc.sum().item())
+    out["mcts_action"] = recommend(mc.cpu().numpy(), mv.cpu().numpy())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    if rank == 0:
+        print("RESULT " + json.dumps(gathered))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,89 @@
+"""GPU tests of the plugin surface: the drop-in agents return the reference's
+plans on identical seeds (golden vectors) through plan()/act()."""
+import numpy as np
+import pytest
+
+from oracle import envs as oenvs
+from oracle import planners
+from tests.util import load_golden, load_mdps
+
+pytestmark = pytest.mark.gpu
+G = load_golden("golden_finite.json")
+H = load_golden("golden_highway.json")
+M = load_mdps()
+
+
+def finite_env(state=0):
+    from rl_agents_b200.envs import FiniteMDPEnv
+    return FiniteMDPEnv(M["large1_T"], M["large1_R"], M["large1_term"], state=state)
+
+
+def test_opd_agent_finite_matches_reference():
+    from rl_agents_b200.agents.tree_search.deterministic import DeterministicPlannerAgent
+    g = G["opd"]["large1_b500_g0.9"]
+    agent = DeterministicPlannerAgent(finite_env(), {"budget": 500, "gamma": 0.9})
+    agent.seed(0)
+    assert agent.plan(None) == g["plan"]
+    assert agent.act(None) == g["plan"][0]
+    g = G["opd"]["large1_b75_g0.7"]
+    agent = DeterministicPlannerAgent(finite_env(), {"budget": 75, "gamma": 0.7})
+    agent.seed(0)
+    assert agent.plan(None) == g["plan"]
+
+
+def test_opd_agent_highway_episode_with_preprocessor_and_receding_horizon():
+    from rl_agents_b200.agents.tree_search.deterministic import DeterministicPlannerAgent
+    from rl_agents_b200.envs import HighwayLiteEnv
+    env = HighwayLiteEnv(seed=0)
+    cfg = {"budget": 75, "gamma": 0.7, "env_preprocessors": [{"method": "simplify"}], "receding_horizon": 2}
+    agent = DeterministicPlannerAgent(env, cfg)
+    agent.seed(0)
+    g = H["opd"]["s0_b75_g0.7"]
+    first = agent.plan(env.observation())
+    assert first == g["plan"]
+    # drive a short episode: env.step on the CUDA transition, oracle env in lock-step
+    oenv = oenvs.HighwayLite(seed=0)
+    actions = first
+    for k in range(4):
+        obs, r, term, trunc, _ = env.step(actions[0])
+        _, r2, term2, trunc2, _ = oenv.step(actions[0])
+        assert (r, term, trunc) == (r2, term2, trunc2)
+        assert env.words.tolist() == oenv.state.pack().tolist()
+        if term:
+            break
+        prev = actions
+        actions = agent.plan(obs)
+        if k % 2 == 0:                       # receding_horizon = 2: every other call reuses the plan
+            assert actions == prev[1:]
+        else:                                # replanned on the device from the new scene
+            plan, _ = planners.opd_plan(oenvs.HighwayLite(oenv.state.copy()), 75, 0.7,
+                                        np_random=np.random.default_rng(0))
+            assert actions[:1] == plan[:1] or len(plan) == 0
+
+
+def test_mcts_agent_matches_reference_and_keeps_rng_in_sync():
+    from rl_agents_b200.agents.tree_search.mcts import MCTSAgent
+    g = G["mcts"]["large1_b400_g0.8"]
+    agent = MCTSAgent(finite_env(), {"budget": 400, "gamma": 0.8})
+    agent.seed(g["seed"])
+    assert agent.plan(None) == g["plan"]
+    # a second decision continues the same stream the reference would continue
+    ref_rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(g["seed"])))
+    env = oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"])
+    planners.mcts_plan(env, g["episodes"], g["horizon"], 0.8, g["temperature"], ref_rng)
+    plan2, _ = planners.mcts_plan(env, g["episodes"], g["horizon"], 0.8, g["temperature"], ref_rng)
+    assert agent.plan(None) == plan2
+
+
+def test_vi_agent_matches_reference():
+    from rl_agents_b200.agents.dynamic_programming.value_iteration import ValueIterationAgent
+    g = G["vi"]["large1_g0.9_it100"]
+    agent = ValueIterationAgent(finite_env(), {"gamma": 0.9, "iterations": 100})
+    assert np.array_equal(agent.state_action_value, np.array(g["q"]))
+    assert agent.act(0) == g["act0"] == 3
+    assert agent.plan(0) == [3]
+    # non-finite env path: to_finite_mdp() re-solved on every act (value_iteration.py:31-34)
+    agent2 = ValueIterationAgent(oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"]),
+                                 {"gamma": 1.0, "iterations": 2})
+    assert np.array_equal(agent2.state_action_value, np.array(G["vi"]["large1_g1.0_it2"]["q"]))
+    assert agent2.act(None) == 3

@@ -314,3 +314,70 @@ def test_mcts_highway_batch_vs_oracle():
         assert plans[i] == plan
         assert d["parent"].tolist() == t.parent and d["count"].tolist() == t.count and d["action"].tolist() == t.action
         assert np.array_equal(d["value"], np.array(t.value))
+
+
+# ----------------------------------------------------------------- OLOP ----
+@pytest.mark.parametrize("key", sorted(G["olop"]))
+def test_olop_finite_golden(key):
+    """Node order / counts bit-exact; mu_ucb and value_upper within 1e-9 (the KL
+    Newton solve uses log(): CUDA's and numpy's differ by at most an ulp)."""
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.agents.tree_search.mcts import allocation
+    from rl_agents_b200.engine.mcts import pcg64_words
+    from rl_agents_b200.engine.olop import OLOPEngine
+    g = G["olop"][key]
+    cfg = g["config"]
+    episodes, horizon = allocation(max(5, cfg["budget"]), cfg["gamma"])
+    assert (episodes, horizon) == (g["episodes"], g["horizon"])
+    eng = OLOPEngine(_lib.ENV_FINITE, 1, 5, episodes, horizon, cfg["gamma"], cfg["upper_bound"],
+                     cfg["continuation_type"], mdp=product_mdp())
+    gen = np_random(g["seed"])
+    eng.plan(torch.tensor([0], dtype=torch.int32, device="cuda"), pcg64_words(gen).reshape(1, -1))
+    plans, res, rng_words = eng.finish()
+    assert plans[0] == g["plan"]
+    assert_tree_matches(eng.tree_dict(0), g["tree"], ["cumulative_reward", "mu_ucb", "upper"], exact=False,
+                        rtol=1e-9, atol=1e-12)
+
+
+def test_olop_highway_vs_oracle():
+    import torch
+    from oracle import ref_loader
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.mcts import pcg64_words
+    from rl_agents_b200.engine.olop import OLOPEngine
+    ub = {"type": "kullback-leibler", "time": "global", "threshold": "2*np.log(time)"}
+    seeds = [30, 31, 32]
+    words = [oenvs.make_highway_state(s).pack() for s in seeds]
+    eng = OLOPEngine(_lib.ENV_HIGHWAY, len(seeds), 5, 12, 4, 0.8, ub, "uniform")
+    eng.plan(torch.tensor(np.stack(words), dtype=torch.int32, device="cuda"),
+             np.stack([pcg64_words(np_random(7 + i)) for i in range(len(seeds))]))
+    plans, res, _ = eng.finish()
+    for i, s in enumerate(seeds):
+        rng, _ = ref_loader.legacy_np_random(7 + i)
+        plan, t = planners.olop_plan(oenvs.LegacyStepEnv(oenvs.HighwayLite(seed=s)), 0, 0.8, rng, upper_bound=ub,
+                                     continuation_type="uniform", episodes=12, horizon=4)
+        d = eng.tree_dict(i)
+        assert plans[i] == plan
+        assert d["parent"].tolist() == t.parent and d["count"].tolist() == t.count and d["action"].tolist() == t.action
+        np.testing.assert_allclose(d["upper"], np.array(t.upper), rtol=1e-9)
+        np.testing.assert_allclose(d["cumulative_reward"], np.array(t.cumulative_reward, dtype=float), rtol=0, atol=0)
+
+
+def test_olop_default_hoeffding_is_degenerate_like_the_reference():
+    """The reference implements only the KL bound: with the DEFAULT config mu_ucb stays
+    inf (olop.py:153-163) and the plan is all zeros."""
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.mcts import pcg64_words
+    from rl_agents_b200.engine.olop import OLOPEngine
+    ub = {"type": "hoeffding", "time": "global", "threshold": "4*np.log(time)"}
+    eng = OLOPEngine(_lib.ENV_FINITE, 1, 5, 14, 6, 0.8, ub, "zeros", mdp=product_mdp())
+    eng.plan(torch.tensor([0], dtype=torch.int32, device="cuda"), pcg64_words(np_random(0)).reshape(1, -1))
+    plans, res, _ = eng.finish()
+    from oracle import ref_loader
+    rng, _ = ref_loader.legacy_np_random(0)
+    plan, t = planners.olop_plan(oenvs.LegacyStepEnv(oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"])),
+                                 100, 0.8, rng, upper_bound=ub, continuation_type="zeros")
+    assert plans[0] == plan == [0] * 6
+    assert eng.tree_dict(0)["count"].tolist() == t.count

@@ -1,0 +1,142 @@
+"""CPU tests: the C ABI library exports what include/b2_planner.h declares, the
+spec constants in the CUDA header equal the oracle's fp32 values, and the host
+side of the plugin surface (config merge, defaults, allocation, env hand-off,
+the reference's own agent_factory) behaves like the reference's."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import envs as oenvs
+from oracle import ref_loader
+from tests.util import load_golden, load_mdps
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+M = load_mdps()
+
+
+def test_library_exports_every_declared_symbol():
+    from rl_agents_b200 import _lib, build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "b2_planner.h")).read()
+    declared = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()          # resolves every symbol or raises
+    assert lib.b2_version() >= 100
+    assert lib.b2_last_error() is not None
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from rl_agents_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libb2planner.so")
+    with pytest.raises(_lib.B2Error):
+        _lib.load()
+
+
+def test_highway_constants_match_the_spec():
+    src = open(os.path.join(ROOT, "rl_agents_b200", "csrc", "highway_lite.cuh")).read()
+    consts = dict(re.findall(r"HW_CONST\((\w+),\s*(-?0x[0-9a-fA-F.]+p[+-]?\d+)f\)", src))
+    assert len(consts) >= 25
+    for name, lit in consts.items():
+        assert np.float32(float.fromhex(lit)) == getattr(oenvs, name), name
+        assert float.fromhex(lit) == float(np.float32(float.fromhex(lit))), name   # exactly an fp32 value
+
+    def poly(fn):
+        body = src[src.index("float %s(" % fn):]
+        body = body[:body.index("return")]
+        return [np.float32(float.fromhex(x)) for x in re.findall(r"(-?0x[0-9a-fA-F.]+p[+-]?\d+)f", body)]
+    assert poly("asin_p") == oenvs.ASIN_C[::-1]
+    assert poly("sin_p") == oenvs.SIN_C[::-1]
+    assert poly("cos_p") == oenvs.COS_C[::-1]
+
+
+def test_configurable_merges_and_writes_back():
+    from rl_agents_b200.configuration import Configurable
+
+    class C(Configurable):
+        @classmethod
+        def default_config(cls):
+            return {"a": 1, "nested": {"x": 1, "y": 2}}
+    user = {"nested": {"y": 5}, "extra": "kept"}
+    c = C(user)
+    assert c.config == {"a": 1, "nested": {"x": 1, "y": 5}, "extra": "kept"}
+    assert user == c.config        # configuration.py:12-18: the caller's dict is completed
+
+
+def test_agent_defaults_match_reference_defaults():
+    from rl_agents_b200.agents.tree_search.deterministic import DeterministicPlannerAgent
+    from rl_agents_b200.agents.tree_search.mcts import MCTSAgent, allocation
+    env = oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"])
+    a = DeterministicPlannerAgent(env, {})
+    assert a.config == {"env_preprocessors": [], "display_tree": False, "receding_horizon": 1, "terminal_reward": 0,
+                        "budget": 500, "gamma": 0.8, "step_strategy": "reset"}
+    m = MCTSAgent(env, {"unknown_key": 3})
+    assert m.config["budget"] == 100 and m.config["temperature"] == 2 / (1 - 0.8) and m.config["closed_loop"] is False
+    assert (m.planner.config["episodes"], m.planner.config["horizon"]) == (14, 6) and m.config["unknown_key"] == 3
+    for key, (ep, hz) in load_golden("golden_finite.json")["allocation"].items():
+        b, g = key.split("_")
+        assert allocation(int(b), float(g)) == (ep, hz)
+    from rl_agents_b200.agents.tree_search.olop import OLOPAgent
+    o = OLOPAgent(env, {"budget": 500, "gamma": 0.7})
+    assert (o.planner.config["episodes"], o.planner.config["horizon"]) == (72, 6)
+    assert o.config["upper_bound"] == {"type": "hoeffding", "time": "global", "threshold": "4*np.log(time)"}
+    assert o.config["continuation_type"] == "zeros"
+    assert a.save("x") is False and a.load("x") is False and a.seed(3) == [3]
+    with pytest.raises(ValueError):
+        MCTSAgent(env, {"rollout_policy": {"type": "nope"}})
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not present")
+def test_reference_defaults_and_factory_accept_the_drop_in():
+    """The reference's own loader (factory.py:12-27) builds our agents from a
+    `__class__` string, and their completed configs equal the reference agents'."""
+    ref_loader.load_reference()
+    from rl_agents.agents.common.abstract import AbstractAgent as RefAbstractAgent
+    from rl_agents.agents.common.factory import agent_factory
+    from rl_agents.agents.tree_search.deterministic import DeterministicPlannerAgent as RefOPD
+    from rl_agents.agents.tree_search.mcts import MCTSAgent as RefMCTS
+    env = oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"])
+    for path, ref_cls, cfg in [
+            ("rl_agents_b200.agents.tree_search.deterministic.DeterministicPlannerAgent", RefOPD, {"budget": 75}),
+            ("rl_agents_b200.agents.tree_search.mcts.MCTSAgent", RefMCTS, {"budget": 400, "gamma": 0.9})]:
+        mine = agent_factory(env, dict(cfg, __class__="<class '%s'>" % path))
+        ref = ref_cls(env, dict(cfg))
+        theirs = dict(ref.config)
+        ours = {k: v for k, v in mine.config.items() if k != "__class__"}
+        assert ours == theirs
+        assert isinstance(mine, RefAbstractAgent)
+        assert mine.config.get("gamma", 1) == theirs["gamma"]     # evaluation.py:327 reads it
+
+
+def test_env_adapters():
+    from rl_agents_b200.envs import FiniteMDPEnv, HighwayLiteEnv
+    from rl_agents_b200.envs.adapters import describe
+    from rl_agents_b200.envs.highway_lite import available_actions, make_scene
+    from rl_agents_b200 import _lib
+    fe = FiniteMDPEnv(M["large1_T"], M["large1_R"], M["large1_term"], state=7)
+    d = describe(fe)
+    assert (d.kind, d.n_actions, d.root.tolist()) == (_lib.ENV_FINITE, 5, [7])
+    d2 = describe(oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"], state=3))   # duck-typed .mdp
+    assert d2.root.tolist() == [3]
+    he = HighwayLiteEnv(seed=4)
+    d3 = describe(he.simplify())
+    assert d3.kind == _lib.ENV_HIGHWAY and d3.root.tolist() == oenvs.make_highway_state(4).pack().tolist()
+    for seed in range(20):
+        assert available_actions(make_scene(seed)) == oenvs.highway_available_actions(oenvs.make_highway_state(seed))
+    with pytest.raises(TypeError):
+        class Weird(object):
+            action_space = fe.action_space
+            unwrapped = property(lambda self: self)
+        describe(Weird())
+
+
+def test_finite_env_steps_like_the_oracle_env():
+    from rl_agents_b200.envs import FiniteMDPEnv
+    a = FiniteMDPEnv(M["large1_T"], M["large1_R"], M["large1_term"])
+    b = oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"])
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        act = int(rng.integers(5))
+        assert a.step(act) == b.step(act)
