@@ -118,10 +118,12 @@ class LegacyStepEnv(object):
         return self.env.get_available_actions()
 
     def __getattr__(self, name):
-        if name in ("env", "action_space"):
+        if name in ("env", "action_space") or name.startswith("__"):
             raise AttributeError(name)
-        attr = getattr(self.env, name)
-        return attr
+        return getattr(self.env, name)
+
+    def __deepcopy__(self, memo):
+        return LegacyStepEnv(copy.deepcopy(self.env, memo))
 
     def step(self, action):
         obs, r, done, trunc, info = self.env.step(action)
