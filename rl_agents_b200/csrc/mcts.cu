@@ -33,7 +33,7 @@ struct FiniteEnv {
     __device__ __forceinline__ void load_root(const MctsArgs& a, int tree, int li) { s = a.root_states[tree]; }
     __device__ __forceinline__ int avail(const MctsArgs& a, unsigned gmask) const { return (1 << a.cfg.n_actions) - 1; }
     __device__ __forceinline__ static int nth(int mask, int n) { return n; }
-    __device__ __forceinline__ double step(const MctsArgs& a, int action, int li, unsigned gmask, bool& term, bool& trunc) {
+    __device__ __forceinline__ double step(const MctsArgs& a, int action, int li, unsigned gmask, float* gs, bool& term, bool& trunc) {
         const b2_finite_mdp& m = a.cfg.mdp;
         const double r = m.reward[(int64_t)s * m.n_actions + action];
         s = m.transition[(int64_t)s * m.n_actions + action];
@@ -55,8 +55,8 @@ struct HighwayEnv {
         return hw::avail_mask(ego_y, si);
     }
     __device__ __forceinline__ static int nth(int mask, int n) { return hw::nth_action(mask, n); }
-    __device__ __forceinline__ double step(const MctsArgs& a, int action, int li, unsigned gmask, bool& term, bool& trunc) {
-        return (double)hw::step(L, li, t, si, action, term, trunc, gmask);
+    __device__ __forceinline__ double step(const MctsArgs& a, int action, int li, unsigned gmask, float* gs, bool& term, bool& trunc) {
+        return (double)hw::step(L, li, t, si, action, term, trunc, gmask, gs);
     }
 };
 
@@ -64,6 +64,7 @@ struct HighwayEnv {
 template <class Env>
 __global__ void __launch_bounds__(128) mcts_kernel(MctsArgs a) {
     constexpr int G = Env::GROUP;
+    __shared__ float scratch[G == 16 ? 128 / 16 : 1][hw::SCRATCH_FLOATS];
     const int gtid = blockIdx.x * 128 + threadIdx.x;
     const int tree_raw = gtid / G, li = gtid % G;
     const bool live = tree_raw < a.cfg.n_trees;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(128) mcts_kernel(MctsArgs a) {
             }
             bool term, trunc;
             Env next = env;
-            const double r = next.step(a, action, li, gmask, term, trunc);
+            const double r = next.step(a, action, li, gmask, scratch[(threadIdx.x >> 4) % (128 / 16)], term, trunc);
             if (active) {
                 env = next;
                 ++env_steps;

@@ -67,7 +67,7 @@ struct OFiniteEnv {
     __device__ __forceinline__ void load_root(const OlopArgs& a, int tree, int li) { s = a.root_states[tree]; }
     __device__ __forceinline__ int avail(const OlopArgs& a, unsigned gmask) const { return (1 << a.cfg.n_actions) - 1; }
     __device__ __forceinline__ static int nth(int mask, int n) { return n; }
-    __device__ __forceinline__ double step(const OlopArgs& a, int action, int li, unsigned gmask, bool& term) {
+    __device__ __forceinline__ double step(const OlopArgs& a, int action, int li, unsigned gmask, float* gs, bool& term) {
         const b2_finite_mdp& m = a.cfg.mdp;
         const double r = m.reward[(int64_t)s * m.n_actions + action];
         s = m.transition[(int64_t)s * m.n_actions + action];
@@ -87,15 +87,16 @@ struct OHighwayEnv {
         return hw::avail_mask(__shfl_sync(gmask, L.y, 0, 16), si);
     }
     __device__ __forceinline__ static int nth(int mask, int n) { return hw::nth_action(mask, n); }
-    __device__ __forceinline__ double step(const OlopArgs& a, int action, int li, unsigned gmask, bool& term) {
+    __device__ __forceinline__ double step(const OlopArgs& a, int action, int li, unsigned gmask, float* gs, bool& term) {
         bool trunc;
-        return (double)hw::step(L, li, t, si, action, term, trunc, gmask);
+        return (double)hw::step(L, li, t, si, action, term, trunc, gmask, gs);
     }
 };
 
 template <class Env>
 __global__ void __launch_bounds__(128) olop_kernel(OlopArgs a) {
     constexpr int G = Env::GROUP;
+    __shared__ float scratch[G == 16 ? 128 / 16 : 1][hw::SCRATCH_FLOATS];
     const int gtid = blockIdx.x * 128 + threadIdx.x;
     const int tree_raw = gtid / G, li = gtid % G;
     const bool live = tree_raw < a.cfg.n_trees;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(128) olop_kernel(OlopArgs a) {
                 action = tr.meta[nb + child] & 0xff;
             }
             bool term;
-            const double r = env.step(a, action, li, gmask, term);     // olop.py:87
+            const double r = env.step(a, action, li, gmask, scratch[(threadIdx.x >> 4) % (128 / 16)], term);     // olop.py:87
             if (live && !error) {
                 node = child;
                 // update (olop.py:132-142)

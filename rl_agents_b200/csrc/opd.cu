@@ -264,6 +264,7 @@ constexpr int HW_THREADS = 96;
 __global__ void __launch_bounds__(HW_THREADS) opd_highway_kernel(OpdArgs a) {
     extern __shared__ double smem_d[];
     __shared__ Shared sh;
+    __shared__ float hw_scratch[HW_THREADS / 16][hw::SCRATCH_FLOATS];
     const int tree_id = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid >> 4, li = tid & 15;
     const int64_t nb = (int64_t)tree_id * a.cfg.node_capacity;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(HW_THREADS) opd_highway_kernel(OpdArgs a) {
         const int n = __popc(mask);
         const int action = grp < n ? hw::nth_action(mask, grp) : hw::A_IDLE;
         bool term, trunc;
-        const float r = hw::step(L, li, t, si, action, term, trunc);
+        const float r = hw::step(L, li, t, si, action, term, trunc, 0xffffffffu, hw_scratch[grp]);
         if (grp < n) {
             hw::store_state(states + (int64_t)(n_nodes + grp) * hw::WORDS, li, L, t, si);
             if (li == 0) {
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(HW_THREADS) opd_highway_kernel(OpdArgs a) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) highway_step_kernel(int32_t* states, const int32_t* actions, float* reward,
                                                            int32_t* flags, int32_t* avail, int n_envs) {
+    __shared__ float hw_scratch[128 / 16][hw::SCRATCH_FLOATS];
     const int g = (blockIdx.x * 128 + threadIdx.x) >> 4, li = threadIdx.x & 15;
     const bool live = g < n_envs;
     const int e = live ? g : n_envs - 1;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(128) highway_step_kernel(int32_t* states, cons
     int t, si;
     hw::load_state(states + (int64_t)e * hw::WORDS, li, L, t, si);
     bool term, trunc;
-    const float r = hw::step(L, li, t, si, actions[e], term, trunc);
+    const float r = hw::step(L, li, t, si, actions[e], term, trunc, 0xffffffffu, hw_scratch[threadIdx.x >> 4]);
     const float ego_y = __shfl_sync(0xffffffffu, L.y, 0, 16);
     if (live) {
         hw::store_state(states + (int64_t)e * hw::WORDS, li, L, t, si);
