@@ -6,7 +6,7 @@
 
 Workload (BASELINE.json configs[1], C2): DeterministicPlannerAgent / OPD, budget
 10 000 (=> 2 000 expand() calls per decision), gamma 0.8, on a batch of
-`--trees` independent decisions (seeded scenes) per GPU -- one search tree per
+`--trees` independent decisions (seeded scenes) per GPU -- eight search trees per
 CTA, strict best-first order inside every tree (bit-exact with the reference).
 A "step" is one plan() of the whole batch.  `value` = expand() calls per second
 over all GPUs with the root scenes resident in HBM; `e2e` = the same through
@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--trees", type=int, default=0, help="decisions per GPU per step (default 8 per SM)")
+    ap.add_argument("--trees", type=int, default=0, help="decisions per GPU per step (default 24 per SM)")
     ap.add_argument("--budget", type=int, default=BUDGET)
     ap.add_argument("--gamma", type=float, default=GAMMA)
     ap.add_argument("--keys-in-smem", type=int, default=0)
@@ -173,7 +173,7 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    trees = a.trees or 8 * sms
+    trees = a.trees or 24 * sms
     n_exp = a.budget // N_ACTIONS
 
     eng = OPDEngine(_lib.ENV_HIGHWAY, trees, N_ACTIONS, a.budget, a.gamma, keys_in_smem=bool(a.keys_in_smem),

@@ -320,6 +320,124 @@ __global__ void __launch_bounds__(HW_THREADS) opd_highway_kernel(OpdArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// HighwayLite, batched: 8 trees per CTA (one warp owns one tree for select /
+// commit / finish); the children of all 8 expansions of an iteration are packed
+// densely onto the CTA's 16 half-warp groups, so that ~94 % of the simulation
+// slots do real work (a lone tree fills 3.8 of its 6 slots).  Node order inside
+// every tree is unchanged: the trees are independent, only the slots are shared.
+// ---------------------------------------------------------------------------
+constexpr int MT_TREES = 8;
+constexpr int MT_THREADS = 256;
+constexpr int MT_GROUPS = MT_THREADS / 16;
+
+struct MultiShared {
+    Shared sh[MT_TREES];
+    int n[MT_TREES];          // children of this iteration's expansion (0: tree idle / dead)
+    int mask[MT_TREES];       // available-action mask of the expanded leaf
+    int n_nodes[MT_TREES], max_depth[MT_TREES], term_exp[MT_TREES], n_exp[MT_TREES], dead[MT_TREES];
+};
+
+__global__ void __launch_bounds__(MT_THREADS, 3) opd_highway_multi_kernel(OpdArgs a) {
+    extern __shared__ double smem_d[];
+    __shared__ MultiShared ms;
+    __shared__ float hw_scratch[MT_GROUPS][hw::SCRATCH_FLOATS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = tid >> 4, li = tid & 15;
+    const int tree0 = blockIdx.x * MT_TREES;
+    const int n_local = min(MT_TREES, a.cfg.n_trees - tree0);
+    // the warp's own tree
+    const int my_tree = tree0 + warp;
+    const bool owner = warp < n_local;
+    const int64_t my_nb = (int64_t)my_tree * a.cfg.node_capacity;
+    char* my_ws = a.workspace + (int64_t)(owner ? my_tree : tree0) * a.lay.ws_bytes_per_tree;
+    Tournament T;
+    setup_tournament(T, a.lay, smem_d + (size_t)warp * a.lay.smem_doubles, (double*)my_ws);
+    int32_t* my_exp_order = (int32_t*)(my_ws + a.lay.ws_doubles * 8);
+    if (owner) {
+        init_tree(a, T, my_nb, lane, 32);
+        int32_t* st = a.tree.state + my_nb * hw::WORDS;
+        for (int i = lane; i < hw::WORDS; i += 32) st[i] = a.root_states[(int64_t)my_tree * hw::WORDS + i];
+    }
+    if (lane == 0) {
+        ms.sh[warp].error = 0;
+        ms.n[warp] = 0;
+        ms.n_nodes[warp] = 1; ms.max_depth[warp] = 0; ms.term_exp[warp] = 0; ms.n_exp[warp] = 0;
+        ms.dead[warp] = owner ? 0 : 1;
+    }
+    __syncthreads();
+    for (int it = 0; it < a.cfg.n_expansions; ++it) {
+        // ---- phase 1: every warp selects the leaf of its own tree ----
+        if (!ms.dead[warp]) {
+            const int leaf = T.select(lane);
+            if (lane == 0) {
+                Shared& sh = ms.sh[warp];
+                sh.leaf = leaf;
+                sh.depth = a.tree.depth[my_nb + leaf];
+                sh.lower = a.tree.lower[my_nb + leaf];
+                sh.done_parent = (a.tree.meta[my_nb + leaf] >> 16) & 1;
+                const int32_t* w = a.tree.state + (my_nb + leaf) * hw::WORDS;
+                const int mask = hw::avail_mask(__int_as_float(w[hw::V]), w[8 * hw::V + 1]);
+                ms.mask[warp] = mask;
+                ms.n[warp] = __popc(mask);
+            }
+        } else if (lane == 0) {
+            ms.n[warp] = 0;
+        }
+        __syncthreads();
+        // ---- phase 2: pack the children of all trees onto the groups ----
+        int offs[MT_TREES + 1];
+        offs[0] = 0;
+#pragma unroll
+        for (int u = 0; u < MT_TREES; ++u) offs[u + 1] = offs[u] + ms.n[u];
+        const int total = offs[MT_TREES];
+        for (int base = 0; base < total; base += MT_GROUPS) {
+            if (base + 2 * warp >= total) continue;          // neither group of this warp has work
+            const int slot = base + grp;
+            const bool real = slot < total;
+            int tr = 0;
+#pragma unroll
+            for (int u = 1; u < MT_TREES; ++u) tr += (real && slot >= offs[u]) ? 1 : 0;
+            const int k = real ? slot - offs[tr] : 0;
+            const int64_t nb = (int64_t)(tree0 + tr) * a.cfg.node_capacity;
+            int32_t* states = a.tree.state + nb * hw::WORDS;
+            const Shared& sh = ms.sh[tr];
+            hw::Lane L;
+            int t, si;
+            hw::load_state(states + (int64_t)sh.leaf * hw::WORDS, li, L, t, si);
+            const int action = real ? hw::nth_action(ms.mask[tr], k) : hw::A_IDLE;
+            bool term, trunc;
+            const float r = hw::step(L, li, t, si, action, term, trunc, 0xffffffffu, hw_scratch[grp]);
+            if (real) {
+                hw::store_state(states + (int64_t)(ms.n_nodes[tr] + k) * hw::WORDS, li, L, t, si);
+                if (li == 0) {
+                    ms.sh[tr].child_reward[k] = (double)r;
+                    ms.sh[tr].child_done[k] = term ? 1 : 0;
+                    ms.sh[tr].child_action[k] = action;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: every warp commits its own tree ----
+        if (!ms.dead[warp]) {
+            Shared& sh = ms.sh[warp];
+            const int n = ms.n[warp], c0 = ms.n_nodes[warp];
+            commit_expansion(a, T, sh, my_nb, sh.leaf, c0, n, ms.n_exp[warp], my_exp_order, lane);
+            __syncwarp();
+            if (lane == 0) {
+                ms.term_exp[warp] += sh.done_parent;
+                ms.max_depth[warp] = max(ms.max_depth[warp], sh.depth + 1);
+                ms.n_nodes[warp] = c0 + n;
+                ms.n_exp[warp] += 1;
+                if (sh.error) ms.dead[warp] = 1;      // deterministic.py:46-47 raises: stop this tree
+            }
+            __syncwarp();
+        }
+    }
+    if (owner)
+        finish_tree(a, my_nb, my_tree, ms.n_nodes[warp], ms.n_exp[warp], ms.max_depth[warp], ms.term_exp[warp],
+                    ms.sh[warp].error, my_exp_order, lane);
+}
+
+// ---------------------------------------------------------------------------
 // batched env transition (b2_highway_step): one scene per 16-lane group
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) highway_step_kernel(int32_t* states, const int32_t* actions, float* reward,
@@ -413,8 +531,17 @@ extern "C" int b2_opd_plan(const b2_opd_config* cfg, const int32_t* root_states,
         opd_finite_kernel<<<cfg->n_trees, 32, smem, stream>>>(a);
     } else if (cfg->env_kind == B2_ENV_HIGHWAY) {
         B2_REQUIRE(cfg->n_actions == B2_HW_ACTIONS, "HighwayLite has 5 actions");
-        B2_CUDA_CHECK(cudaFuncSetAttribute(opd_highway_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        opd_highway_kernel<<<cfg->n_trees, HW_THREADS, smem, stream>>>(a);
+        const size_t smem_multi = smem * MT_TREES;
+        if (cfg->n_trees >= 2 * MT_TREES && smem_multi <= 64 * 1024) {
+            // batch mode: 8 trees per CTA, children packed densely on the simulation slots
+            B2_CUDA_CHECK(cudaFuncSetAttribute(opd_highway_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem_multi));
+            opd_highway_multi_kernel<<<(cfg->n_trees + MT_TREES - 1) / MT_TREES, MT_THREADS, smem_multi, stream>>>(a);
+        } else {
+            // latency mode: one tree per CTA
+            B2_CUDA_CHECK(cudaFuncSetAttribute(opd_highway_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            opd_highway_kernel<<<cfg->n_trees, HW_THREADS, smem, stream>>>(a);
+        }
     } else {
         set_error("unknown env_kind %d", cfg->env_kind);
         return B2_ERR_INVALID;

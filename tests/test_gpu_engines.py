@@ -262,6 +262,25 @@ def test_opd_highway_batch_vs_oracle():
         assert np.array_equal(d["lower"], np.array(t.lower)) and np.array_equal(d["upper"], np.array(t.upper))
 
 
+def test_opd_highway_packed_batch_equals_single_tree_search():
+    """>= 16 trees take the 8-trees-per-CTA kernel (children of different trees share the
+    simulation slots); every tree must equal the one-tree-per-CTA search and the oracle."""
+    seeds = list(range(40, 59))          # 19 trees: two full CTAs + a partial one
+    words = [oenvs.make_highway_state(s).pack() for s in seeds]
+    eng, plans, res = run_opd_highway(words, 150, 0.8)
+    for i in (0, 7, 8, 18):
+        one, plans1, res1 = run_opd_highway([words[i]], 150, 0.8)
+        a, b = eng.tree_dict(i), one.tree_dict(0)
+        assert plans[i] == plans1[0] and res[i, :7].tolist() == res1[0, :7].tolist()
+        for k in ("parent", "action", "count", "depth", "first_child", "done", "reward", "lower", "upper"):
+            assert np.array_equal(a[k], b[k]), (i, k)
+    for i in (3, 17):
+        plan, t = planners.opd_plan(oenvs.HighwayLite(seed=seeds[i]), 150, 0.8, np_random=np_random(0))
+        d = eng.tree_dict(i)
+        assert plans[i] == plan and d["count"].tolist() == t.count and d["parent"].tolist() == t.parent
+        assert np.array_equal(d["upper"], np.array(t.upper))
+
+
 # ----------------------------------------------------------------- MCTS ----
 def run_mcts(env_kind, roots, episodes, horizon, gamma, temperature, seeds, mdp=None):
     import torch
