@@ -188,6 +188,8 @@ ON_LANE_MARGIN = f32(3.0)             # width/2 + margin 1
 EPS = f32(0.01)
 SPEED_LO = f32(20.0)
 SPEED_RANGE = f32(10.0)
+LAT_DEADBAND = f32(1e-9)              # |lateral error| below this is treated as 0 (m)
+HEADING_DEADBAND = f32(1e-12)         # |heading error| below this is treated as 0 (rad)
 
 # odd/even polynomials (coefficients are frozen fp32 literals, see spec)
 ASIN_C = [f32(x) for x in (0.16666667, 0.075, 0.044642857, 0.030381944,
@@ -416,6 +418,7 @@ def highway_step(state, action):
 
         # ---- steering (all controlled vehicles, ego included) ----
         lat = y - tgt.astype(f32) * LANE_W
+        lat = np.where(np.abs(lat) < LAT_DEADBAND, f32(0.0), lat).astype(f32)
         lat_speed_cmd = -(KP_LATERAL * lat)
         nzv = not_zero(v)
         u = lat_speed_cmd / nzv
@@ -424,6 +427,7 @@ def highway_step(state, action):
         dh = heading_ref - h
         dh = np.where(dh > PI, dh - TWO_PI, dh)
         dh = np.where(dh < -PI, dh + TWO_PI, dh)
+        dh = np.where(np.abs(dh) < HEADING_DEADBAND, f32(0.0), dh).astype(f32)
         rate = KP_HEADING * dh
         sb = (HALF_LENGTH / nzv) * rate
         sb = np.minimum(np.maximum(sb, -S_BETA_MAX), S_BETA_MAX)
