@@ -130,6 +130,27 @@ def test_vi_sparse_random_vs_oracle(S, A, B, seed):
     assert np.array_equal(q.cpu().numpy(), q_ref)
 
 
+@pytest.mark.parametrize("mode,S,A,B,seed", [("sparse", 4096, 8, 4, 0), ("sparse", 1600, 8, 4, 1), ("sparse", 6400, 4, 2, 2),
+                                             ("sparse", 2048, 3, 9, 3), ("deterministic", 2048, 4, 1, 4),
+                                             ("deterministic", 5120, 8, 1, 5)])
+def test_vi_tma_staged_kernel_vs_oracle(mode, S, A, B, seed):
+    """Shapes whose tiles satisfy the 16-byte rules of cp.async.bulk take the TMA-staged kernel
+    (several tiles per CTA, ragged last tile); results stay bit-identical with numpy."""
+    from rl_agents_b200.engine.vi import VIEngine
+    term = np.random.default_rng(seed).uniform(size=S) < 0.03
+    if mode == "sparse":
+        P, N, R = oenvs.garnet(S, A, B, seed=seed)
+        q_ref, sweeps_ref = planners.value_iteration("sparse", P, R, term, 0.9, 25, nxt=N)
+        eng = VIEngine("sparse", P, R, term, nxt=N, gamma=0.9)
+    else:
+        T, R = oenvs.garnet(S, A, 1, seed=seed, deterministic=True)
+        q_ref, sweeps_ref = planners.value_iteration("deterministic", T, R, term, 0.9, 25)
+        eng = VIEngine("deterministic", T, R, term, gamma=0.9)
+    q, sweeps = eng.solve(25)
+    assert sweeps == sweeps_ref
+    assert np.array_equal(q.cpu().numpy(), q_ref)
+
+
 def test_vi_early_exit_returns_previous_iterate():
     from rl_agents_b200.engine.vi import VIEngine
     T, R = oenvs.garnet(400, 4, 1, seed=9, deterministic=True)
