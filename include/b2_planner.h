@@ -69,7 +69,8 @@ typedef struct b2_vi_problem {
     int32_t mode;
     int32_t n_actions;   /* A                                                */
     int32_t n_next;      /* B (sparse), S (stochastic), ignored otherwise    */
-    int32_t reserved;    /* kernel choice: 0 auto, 1 plain tiled, 2 TMA-staged  */
+    int32_t reserved;    /* kernel choice: 0 auto (register kernel when the shape
+                            allows, else tiled), 1 tiled, 2 TMA-staged tiled    */
     int64_t n_states;    /* S of the whole MDP (length of V)                 */
     int64_t row_begin;   /* state slab [row_begin, row_end) owned by the call */
     int64_t row_end;

@@ -139,6 +139,83 @@ __global__ void __launch_bounds__(256, 4) vi_sweep_gather_kernel(SweepArgs g) {
 }
 
 // ---------------------------------------------------------------------------
+// Register variant for the common small shapes (B in {1,2,4,8}, A a power of two
+// <= 32): one thread per (s,a) row keeps its B probabilities, successors and
+// gathered values in registers (16-byte vector loads, all B gathers in flight),
+// sums them in numpy's order, and the max over the A actions of a state is a
+// segmented warp-shuffle reduction -- no shared memory, no block barrier.
+// ---------------------------------------------------------------------------
+template <int B, bool HAS_P>
+__global__ void __launch_bounds__(256) vi_sweep_row_kernel(SweepArgs g) {
+    if (g.sweep > 0 && g.viol[g.sweep - 1] == 0) return;
+    const int64_t n_sa = g.rows * g.A;
+    const int A = g.A;
+    int bad = 0;
+    for (int64_t qi = (int64_t)blockIdx.x * 256 + threadIdx.x; qi - threadIdx.x % 32 < n_sa;
+         qi += (int64_t)gridDim.x * 256) {
+        const bool live = qi < n_sa;
+        double q = -INFINITY;
+        if (live) {
+            int32_t n[B];
+            double p[B], v[B];
+            const int32_t* np = g.N + qi * B;
+            if constexpr (B % 4 == 0) {
+#pragma unroll
+                for (int b = 0; b < B; b += 4) {
+                    const int4 t = __ldcs(reinterpret_cast<const int4*>(np + b));
+                    n[b] = t.x; n[b + 1] = t.y; n[b + 2] = t.z; n[b + 3] = t.w;
+                }
+            } else if constexpr (B == 2) {
+                const int2 t = __ldcs(reinterpret_cast<const int2*>(np));
+                n[0] = t.x; n[1] = t.y;
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; ++b) n[b] = __ldcs(np + b);
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b) v[b] = __ldg(g.v_in + n[b]);
+            if constexpr (HAS_P) {
+                const double* pp = g.P + qi * B;
+                if constexpr (B % 2 == 0) {
+#pragma unroll
+                    for (int b = 0; b < B; b += 2) {
+                        const double2 t = __ldcs(reinterpret_cast<const double2*>(pp + b));
+                        p[b] = t.x; p[b + 1] = t.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < B; ++b) p[b] = __ldcs(pp + b);
+                }
+#pragma unroll
+                for (int b = 0; b < B; ++b) v[b] = p[b] * v[b];
+            }
+            double nv;
+            if constexpr (B < 8) {          // numpy pairwise_sum, n < 8: sequential from 0.
+                nv = 0.;
+#pragma unroll
+                for (int b = 0; b < B; ++b) nv += v[b];
+            } else {                         // n == 8: eight accumulators, fixed combination tree
+                nv = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            }
+            const int64_t srow = qi / A;
+            if (g.term[srow]) nv = 0.0;
+            q = __ldcs(g.R + qi) + g.gamma * nv;
+            if (!np_isclose(__ldcs(g.q_old + qi), q, g.rtol, g.atol)) bad++;
+            __stcs(g.q_new + qi, q);
+        }
+        // V' = max_a Q': the A actions of a state sit in A consecutive lanes
+        double m = q;
+        for (int o = 1; o < A; o <<= 1) {
+            const double w = __shfl_xor_sync(0xffffffffu, m, o);
+            m = w > m ? w : m;
+        }
+        if (live && (qi % A) == 0) g.v_out[g.row_begin + qi / A] = m;
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(g.viol + g.sweep, bad);
+}
+
+// ---------------------------------------------------------------------------
 // TMA-staged variant of the gather sweep (the default for well-formed shapes).
 // Persistent CTAs; a 3-stage ring of shared-memory tiles is filled by bulk async
 // copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) issued by one
@@ -340,6 +417,21 @@ extern "C" int b2_vi_sweep(const b2_vi_problem* p, const double* v_in, const dou
     }
     const int E = g.A * g.B;
     B2_REQUIRE(E <= 8192, "n_actions * n_next > 8192 not supported by the tiled kernel");
+    // register kernel: B in {1,2,4,8}, A a power of two <= 32, vector-load alignment
+    if (p->reserved == 0 && (g.A & (g.A - 1)) == 0 && g.A <= 32 && (g.B == 1 || g.B == 2 || g.B == 4 || g.B == 8) &&
+        (uintptr_t)g.N % 16 == 0 && (!g.P || (uintptr_t)g.P % 16 == 0)) {
+        const int64_t n_sa = g.rows * g.A;
+        const int64_t blocks = (n_sa + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 64;
+        const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+#define B2_ROW(BB)                                                                            \
+    if (g.P) vi_sweep_row_kernel<BB, true><<<grid, 256, 0, stream>>>(g);                      \
+    else vi_sweep_row_kernel<BB, false><<<grid, 256, 0, stream>>>(g)
+        if (g.B == 1) { B2_ROW(1); } else if (g.B == 2) { B2_ROW(2); } else if (g.B == 4) { B2_ROW(4); } else { B2_ROW(8); }
+#undef B2_ROW
+        B2_CUDA_CHECK(cudaGetLastError());
+        return B2_OK;
+    }
     {
         // TMA-staged kernel: tiles of TS states (TS % 16 == 0 keeps every bulk copy 16-byte sized/aligned;
         // the last, ragged tile must still satisfy that, else fall back to the plain kernel)

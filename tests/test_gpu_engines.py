@@ -132,10 +132,11 @@ def test_vi_sparse_random_vs_oracle(S, A, B, seed):
 
 @pytest.mark.parametrize("mode,S,A,B,seed", [("sparse", 4096, 8, 4, 0), ("sparse", 1600, 8, 4, 1), ("sparse", 6400, 4, 2, 2),
                                              ("sparse", 2048, 3, 9, 3), ("deterministic", 2048, 4, 1, 4),
-                                             ("deterministic", 5120, 8, 1, 5)])
-def test_vi_tma_staged_kernel_vs_oracle(mode, S, A, B, seed):
-    """Shapes whose tiles satisfy the 16-byte rules of cp.async.bulk take the TMA-staged kernel
-    (several tiles per CTA, ragged last tile); results stay bit-identical with numpy."""
+                                             ("deterministic", 5120, 8, 1, 5), ("sparse", 3200, 8, 8, 6)])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_vi_kernel_variants_vs_oracle(mode, S, A, B, seed, kernel):
+    """The three sweep kernels (0: register rows when the shape allows, 1: tiled, 2: TMA-staged
+    tiles with a ragged last tile) all stay bit-identical with numpy."""
     from rl_agents_b200.engine.vi import VIEngine
     term = np.random.default_rng(seed).uniform(size=S) < 0.03
     if mode == "sparse":
@@ -146,6 +147,7 @@ def test_vi_tma_staged_kernel_vs_oracle(mode, S, A, B, seed):
         T, R = oenvs.garnet(S, A, 1, seed=seed, deterministic=True)
         q_ref, sweeps_ref = planners.value_iteration("deterministic", T, R, term, 0.9, 25)
         eng = VIEngine("deterministic", T, R, term, gamma=0.9)
+    eng.problem.reserved = kernel
     q, sweeps = eng.solve(25)
     assert sweeps == sweeps_ref
     assert np.array_equal(q.cpu().numpy(), q_ref)
@@ -249,6 +251,38 @@ def test_opd_reward_out_of_range_raises():
         env = oenvs.FiniteMDPLite(M["large1_T"], R, M["large1_term"])
         with pytest.raises(ValueError):
             planners.opd_plan(env, 500, 0.9, np_random=np_random(0))
+
+
+def test_opd_large_budget_invariants():
+    """Budget 2e5 on a finite MDP (C5-sized trees are out of the oracle's reach: the reference is
+    O(budget^2)): frontier keys and the first tournament level live in the global workspace here.
+    Size-independent properties: every expansion creates A children; count(root) = #nodes;
+    count(node) = 2 + #descendants; an internal node's bounds are the max of its children's;
+    children bounds follow the update rule from the parent's creation-time lower bound."""
+    import torch
+    budget, gamma = 200000, 0.95
+    eng, plans, res = run_opd_finite(product_mdp(), budget, gamma, [0, 13])
+    n = 1 + (budget // 5) * 5
+    assert res[:, 0].tolist() == [n, n] and res[:, 1].tolist() == [n - budget // 5] * 2
+    for t in range(2):
+        parent, fc, cnt = eng.parent[t, :n].long(), eng.first_child[t, :n].long(), eng.count[t, :n]
+        lower, upper, meta = eng.lower[t, :n], eng.upper[t, :n], eng.meta[t, :n]
+        internal = fc >= 0
+        assert int(internal.sum()) == budget // 5 and int(cnt[0]) == n
+        assert bool((((meta >> 8) & 0xff)[internal] == 5).all())
+        kids = fc[internal].unsqueeze(1) + torch.arange(5, device=fc.device)
+        assert bool((parent[kids] == torch.nonzero(internal)).all())
+        assert bool((lower[internal] == lower[kids].max(dim=1).values).all())
+        assert bool((upper[internal] == upper[kids].max(dim=1).values).all())
+        sub = (cnt[kids] - 1).sum(dim=1)
+        expect = sub + torch.where(torch.nonzero(internal).squeeze(1) == 0, 1, 2)
+        assert bool((cnt[internal] == expect).all())
+        assert bool((cnt[~internal] == 2).all())
+        assert bool((upper >= lower).all()) and bool((upper[1:] <= upper[parent[1:]] + 1e-12).all())
+    # the same search with the frontier in shared memory where it fits is identical (budget 10k)
+    a, pa, _ = run_opd_finite(product_mdp(), 10000, 0.9, [5], keys_in_smem=True)
+    b, pb, _ = run_opd_finite(product_mdp(), 10000, 0.9, [5], keys_in_smem=False)
+    assert pa == pb and torch.equal(a.upper, b.upper) and torch.equal(a.count, b.count) and torch.equal(a.parent, b.parent)
 
 
 def run_opd_highway(words_list, budget, gamma, keys_in_smem=False):
