@@ -92,8 +92,9 @@ __global__ void __launch_bounds__(128) mcts_kernel(MctsArgs a) {
         bool in_sel = true, active = live;
         double total = 0.0;
         for (int h = 0; h < H; ++h) {
-            // all lanes of the warp evaluate the env step together; `active`
-            // only predicates the bookkeeping
+            // the 16 lanes of a group leave the episode together (terminal / truncated); the
+            // other half of the warp keeps stepping its own scene under its half mask
+            if (!active) break;
             int action = hw::A_IDLE < A ? hw::A_IDLE : 0, child = -1;
             const int amask = env.avail(a, gmask);
             if (active && in_sel && tr.first_child[nb + node] < 0) {

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) vi_sweep_row_kernel(SweepArgs g) {
                 for (int b = 0; b < B; ++b) n[b] = __ldcs(np + b);
             }
 #pragma unroll
-            for (int b = 0; b < B; ++b) v[b] = __ldg(g.v_in + n[b]);
+            for (int b = 0; b < B; ++b) v[b] = __ldcg(g.v_in + n[b]);   // L2 only: V never hits in L1 anyway
             if constexpr (HAS_P) {
                 const double* pp = g.P + qi * B;
                 if constexpr (B % 2 == 0) {
