@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libb2planner.so")
+LIB_PATH = os.environ.get("B2PLANNER_LIB") or os.path.join(HERE, "csrc", "libb2planner.so")   # env: kernel-variant experiments
 
 c_void_p, c_int, c_int32, c_int64, c_double = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32,
                                                ctypes.c_int64, ctypes.c_double)

@@ -337,11 +337,16 @@ struct MultiShared {
     int n_nodes[MT_TREES], max_depth[MT_TREES], term_exp[MT_TREES], n_exp[MT_TREES], dead[MT_TREES];
 };
 
-__global__ void __launch_bounds__(MT_THREADS, 3) opd_highway_multi_kernel(OpdArgs a) {
+#ifndef B2_MT_MIN_BLOCKS
+#define B2_MT_MIN_BLOCKS 4   // 64 registers: 4 CTAs = 32 warps per SM (measured best: 26.8M vs 22.4M at 3)
+#endif
+__global__ void __launch_bounds__(MT_THREADS, B2_MT_MIN_BLOCKS) opd_highway_multi_kernel(OpdArgs a) {
     extern __shared__ double smem_d[];
     __shared__ MultiShared ms;
     __shared__ float hw_scratch[MT_GROUPS][hw::SCRATCH_FLOATS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = tid >> 4, li = tid & 15;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, li = tid & 15;
+    int grp = tid >> 4;
+    asm volatile("" : "+r"(grp));   // keep in a register (else re-derived from SR_TID.X at every scratch access)
     const int tree0 = blockIdx.x * MT_TREES;
     const int n_local = min(MT_TREES, a.cfg.n_trees - tree0);
     // the warp's own tree

@@ -87,3 +87,35 @@ def test_vi_agent_matches_reference():
                                  {"gamma": 1.0, "iterations": 2})
     assert np.array_equal(agent2.state_action_value, np.array(G["vi"]["large1_g1.0_it2"]["q"]))
     assert agent2.act(None) == 3
+
+
+def test_olop_agent_matches_reference():
+    from oracle import ref_loader
+    from rl_agents_b200.agents.tree_search.olop import OLOPAgent
+    g = G["olop"]["large1_b200_g0.9_uniform"]
+    agent = OLOPAgent(finite_env(), dict(g["config"]))
+    agent.seed(g["seed"])
+    assert (agent.planner.config["episodes"], agent.planner.config["horizon"]) == (g["episodes"], g["horizon"])
+    assert agent.plan(None) == g["plan"]
+    d = agent.planner.last_tree.tree_dict(0)
+    assert d["count"].tolist() == g["tree"]["count"] and d["parent"].tolist() == g["tree"]["parent"]
+    np.testing.assert_allclose(d["upper"][0], g["tree"]["upper"][0], rtol=1e-9)     # 7.7121380...
+    # the planner's numpy stream continues exactly where the reference's would
+    rng, _ = ref_loader.legacy_np_random(g["seed"])
+    planners.olop_plan(oenvs.LegacyStepEnv(oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"])),
+                       g["config"]["budget"], g["config"]["gamma"], rng, upper_bound=g["config"]["upper_bound"],
+                       continuation_type=g["config"]["continuation_type"])
+    assert agent.planner.np_random.bit_generator.state["state"] == rng.bit_generator.state["state"]
+
+
+def test_agents_reject_unsupported_envs_and_options():
+    from rl_agents_b200.agents.tree_search.deterministic import DeterministicPlannerAgent
+    from rl_agents_b200.agents.tree_search.mcts import MCTSAgent
+    from rl_agents_b200.envs import FiniteMDPEnv
+    stochastic = FiniteMDPEnv(np.full((3, 2, 3), 1 / 3), np.zeros((3, 2)), mode="stochastic")
+    with pytest.raises(ValueError):
+        DeterministicPlannerAgent(stochastic, {"budget": 10}).plan(None)
+    with pytest.raises(NotImplementedError):
+        MCTSAgent(finite_env(), {"closed_loop": True})
+    with pytest.raises(KeyError):
+        MCTSAgent(finite_env(), {"horizon": 5}).plan(None)        # mcts.py:116-118,180: episodes missing
