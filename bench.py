@@ -37,10 +37,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--trees", type=int, default=0, help="decisions per GPU per step (default 24 per SM)")
+    ap.add_argument("--trees", type=int, default=0, help="decisions per GPU per step (default 64 per SM)")
     ap.add_argument("--budget", type=int, default=BUDGET)
     ap.add_argument("--gamma", type=float, default=GAMMA)
     ap.add_argument("--keys-in-smem", type=int, default=0)
+    ap.add_argument("--kernel", type=int, default=0, help="OPD batch kernel variant (b2_opd_config.reserved)")
     ap.add_argument("--cpu-budget", type=int, default=2500, help="budget of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -173,11 +174,11 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    trees = a.trees or 24 * sms
+    trees = a.trees or 64 * sms
     n_exp = a.budget // N_ACTIONS
 
     eng = OPDEngine(_lib.ENV_HIGHWAY, trees, N_ACTIONS, a.budget, a.gamma, keys_in_smem=bool(a.keys_in_smem),
-                    device=dev)
+                    device=dev, kernel=a.kernel)
     # independent decisions: every (rank, tree) its own seeded scene; two alternating input sets
     host_scenes = [torch.from_numpy(np.stack([make_scene(1_000_000 * s + rank * trees + i) for i in range(trees)]))
                    .pin_memory() for s in range(2)]

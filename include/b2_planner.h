@@ -115,7 +115,8 @@ typedef struct b2_opd_config {
     int32_t node_capacity;  /* per tree, >= 1 + n_expansions * n_actions     */
     int32_t plan_capacity;  /* per tree, >= n_expansions + 1                 */
     int32_t keys_in_smem;   /* 1: frontier keys in shared memory when they fit */
-    int32_t reserved;
+    int32_t reserved;       /* HighwayLite batch kernel: 0 default (8 trees per CTA, packed
+                               slots), 1 one tree per warp                   */
     double terminal_reward; /* config["terminal_reward"] (:60-63)            */
     const double* gamma_pow;     /* [n_expansions+2] gamma**d   (host floats) */
     const double* gamma_pow_div; /* [n_expansions+2] gamma**d / (1 - gamma)   */

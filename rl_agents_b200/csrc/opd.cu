@@ -443,6 +443,80 @@ __global__ void __launch_bounds__(MT_THREADS, B2_MT_MIN_BLOCKS) opd_highway_mult
 }
 
 // ---------------------------------------------------------------------------
+// HighwayLite, batched, warp-autonomous: one tree per WARP.  The warp selects,
+// simulates the children two at a time on its two 16-lane halves, commits and
+// finishes entirely on its own -- no block barrier, no coupling between trees, so
+// the warps of an SM drift apart and hide each other's select/commit latency.
+// ---------------------------------------------------------------------------
+constexpr int WT_WARPS = 4;
+
+#ifndef B2_WT_MIN_BLOCKS
+#define B2_WT_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(WT_WARPS * 32, B2_WT_MIN_BLOCKS) opd_highway_warp_kernel(OpdArgs a) {
+    extern __shared__ double smem_d[];
+    __shared__ Shared shs[WT_WARPS];
+    __shared__ float hw_scratch[WT_WARPS * 2][hw::SCRATCH_FLOATS];
+    const int tid = threadIdx.x, lane = tid & 31, li = tid & 15, half = (tid >> 4) & 1;
+    int warp = tid >> 5;
+    asm volatile("" : "+r"(warp));
+    const int tree_id = blockIdx.x * WT_WARPS + warp;
+    if (tree_id >= a.cfg.n_trees) return;        // whole warp; nothing below synchronises across warps
+    Shared& sh = shs[warp];
+    float* gs = hw_scratch[warp * 2 + half];
+    const int64_t nb = (int64_t)tree_id * a.cfg.node_capacity;
+    char* ws = a.workspace + (int64_t)tree_id * a.lay.ws_bytes_per_tree;
+    Tournament T;
+    setup_tournament(T, a.lay, smem_d + (size_t)warp * a.lay.smem_doubles, (double*)ws);
+    int32_t* exp_order = (int32_t*)(ws + a.lay.ws_doubles * 8);
+    int32_t* states = a.tree.state + nb * hw::WORDS;
+    init_tree(a, T, nb, lane, 32);
+    for (int i = lane; i < hw::WORDS; i += 32) states[i] = a.root_states[(int64_t)tree_id * hw::WORDS + i];
+    if (lane == 0) sh.error = 0;
+    __syncwarp();
+    int n_nodes = 1, max_depth = 0, term_exp = 0, it = 0;
+    for (; it < a.cfg.n_expansions; ++it) {
+        const int leaf = T.select(lane);
+        if (lane == 0) {
+            sh.depth = a.tree.depth[nb + leaf];
+            sh.lower = a.tree.lower[nb + leaf];
+            sh.done_parent = (a.tree.meta[nb + leaf] >> 16) & 1;
+        }
+        // "deep copy" of the parent scene into registers (both halves hold it)
+        hw::Lane P;
+        int pt, psi;
+        hw::load_state(states + (int64_t)leaf * hw::WORDS, li, P, pt, psi);
+        const int mask = hw::avail_mask(__shfl_sync(0xffffffffu, P.y, 0, 16), psi);
+        const int n = __popc(mask);
+        for (int base = 0; base < n; base += 2) {
+            const int k = base + half;
+            const bool real = k < n;
+            const int action = real ? hw::nth_action(mask, k) : hw::A_IDLE;
+            hw::Lane L = P;
+            int t = pt, si = psi;
+            bool term, trunc;
+            const float r = hw::step(L, li, t, si, action, term, trunc, 0xffffffffu, gs);
+            if (real) {
+                hw::store_state(states + (int64_t)(n_nodes + k) * hw::WORDS, li, L, t, si);
+                if (li == 0) {
+                    sh.child_reward[k] = (double)r;
+                    sh.child_done[k] = term ? 1 : 0;
+                    sh.child_action[k] = action;
+                }
+            }
+        }
+        __syncwarp();
+        term_exp += sh.done_parent;
+        max_depth = max(max_depth, sh.depth + 1);
+        commit_expansion(a, T, sh, nb, leaf, n_nodes, n, it, exp_order, lane);
+        n_nodes += n;
+        __syncwarp();
+        if (sh.error) { ++it; break; }
+    }
+    finish_tree(a, nb, tree_id, n_nodes, it, max_depth, term_exp, sh.error, exp_order, lane);
+}
+
+// ---------------------------------------------------------------------------
 // batched env transition (b2_highway_step): one scene per 16-lane group
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) highway_step_kernel(int32_t* states, const int32_t* actions, float* reward,
@@ -537,7 +611,13 @@ extern "C" int b2_opd_plan(const b2_opd_config* cfg, const int32_t* root_states,
     } else if (cfg->env_kind == B2_ENV_HIGHWAY) {
         B2_REQUIRE(cfg->n_actions == B2_HW_ACTIONS, "HighwayLite has 5 actions");
         const size_t smem_multi = smem * MT_TREES;
-        if (cfg->n_trees >= 2 * MT_TREES && smem_multi <= 64 * 1024) {
+        const size_t smem_warp = smem * WT_WARPS;
+        if (cfg->n_trees >= 2 * MT_TREES && smem_warp <= 32 * 1024 && cfg->reserved == 1) {
+            // batch mode, warp-autonomous: one tree per warp, no block barriers
+            B2_CUDA_CHECK(cudaFuncSetAttribute(opd_highway_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem_warp));
+            opd_highway_warp_kernel<<<(cfg->n_trees + WT_WARPS - 1) / WT_WARPS, WT_WARPS * 32, smem_warp, stream>>>(a);
+        } else if (cfg->n_trees >= 2 * MT_TREES && smem_multi <= 64 * 1024) {
             // batch mode: 8 trees per CTA, children packed densely on the simulation slots
             B2_CUDA_CHECK(cudaFuncSetAttribute(opd_highway_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem_multi));

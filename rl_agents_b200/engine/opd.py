@@ -17,7 +17,7 @@ class OPDEngine(object):
     raises the reference's errors and returns the plans."""
 
     def __init__(self, env_kind, n_trees, n_actions, budget, gamma, terminal_reward=0.0, mdp=None,
-                 device="cuda", keys_in_smem=False):
+                 device="cuda", keys_in_smem=False, kernel=0):
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -44,7 +44,7 @@ class OPDEngine(object):
         sshape = shape if env_kind == _lib.ENV_FINITE else shape + (_lib.HW_STATE_WORDS,)
         self.state = torch.empty(sshape, dtype=i32, device=self.device)
         self.cfg = _lib.OPDConfig(env_kind, self.n_trees, self.n_actions, self.n_expansions, self.capacity,
-                                  self.plan_capacity, 1 if keys_in_smem else 0, 0, float(terminal_reward),
+                                  self.plan_capacity, 1 if keys_in_smem else 0, int(kernel), float(terminal_reward),
                                   self.gamma_pow.data_ptr(), self.gamma_pow_div.data_ptr(),
                                   self.tables.struct() if self.tables else _lib.FiniteMDP())
         self.tree = _lib.OPDTree(*[t.data_ptr() for t in (self.parent, self.first_child, self.depth, self.count,

@@ -285,11 +285,11 @@ def test_opd_large_budget_invariants():
     assert pa == pb and torch.equal(a.upper, b.upper) and torch.equal(a.count, b.count) and torch.equal(a.parent, b.parent)
 
 
-def run_opd_highway(words_list, budget, gamma, keys_in_smem=False):
+def run_opd_highway(words_list, budget, gamma, keys_in_smem=False, kernel=0):
     import torch
     from rl_agents_b200 import _lib
     from rl_agents_b200.engine.opd import OPDEngine
-    eng = OPDEngine(_lib.ENV_HIGHWAY, len(words_list), 5, budget, gamma, keys_in_smem=keys_in_smem)
+    eng = OPDEngine(_lib.ENV_HIGHWAY, len(words_list), 5, budget, gamma, keys_in_smem=keys_in_smem, kernel=kernel)
     eng.plan(torch.tensor(np.stack(words_list), dtype=torch.int32, device="cuda"))
     plans, res = eng.finish([np_random(0) for _ in words_list])
     return eng, plans, res
@@ -317,12 +317,14 @@ def test_opd_highway_batch_vs_oracle():
         assert np.array_equal(d["lower"], np.array(t.lower)) and np.array_equal(d["upper"], np.array(t.upper))
 
 
-def test_opd_highway_packed_batch_equals_single_tree_search():
-    """>= 16 trees take the 8-trees-per-CTA kernel (children of different trees share the
-    simulation slots); every tree must equal the one-tree-per-CTA search and the oracle."""
-    seeds = list(range(40, 59))          # 19 trees: two full CTAs + a partial one
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_opd_highway_packed_batch_equals_single_tree_search(kernel):
+    """>= 16 trees take a batch kernel (0: 8 trees per CTA, children of different trees share the
+    simulation slots; 1: one tree per warp); every tree must equal the one-tree-per-CTA search
+    and the oracle."""
+    seeds = list(range(40, 59))          # 19 trees: full CTAs + a partial one
     words = [oenvs.make_highway_state(s).pack() for s in seeds]
-    eng, plans, res = run_opd_highway(words, 150, 0.8)
+    eng, plans, res = run_opd_highway(words, 150, 0.8, kernel=kernel)
     for i in (0, 7, 8, 18):
         one, plans1, res1 = run_opd_highway([words[i]], 150, 0.8)
         a, b = eng.tree_dict(i), one.tree_dict(0)
