@@ -94,7 +94,7 @@ struct OHighwayEnv {
 };
 
 template <class Env>
-__global__ void __launch_bounds__(128) olop_kernel(OlopArgs a) {
+__global__ void __launch_bounds__(128, 8) olop_kernel(OlopArgs a) {
     constexpr int G = Env::GROUP;
     __shared__ float scratch[G == 16 ? 128 / 16 : 1][hw::SCRATCH_FLOATS];
     const int gtid = blockIdx.x * 128 + threadIdx.x;

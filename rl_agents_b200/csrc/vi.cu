@@ -454,11 +454,7 @@ extern "C" int b2_vi_sweep(const b2_vi_problem* p, const double* v_in, const dou
             lay.bytes = (off + 127) & ~127;
             const size_t smem_tma = (size_t)TMA_STAGES * lay.bytes + (size_t)ts * g.A * 8;
             if (smem_tma <= 220 * 1024) {
-                static bool tma_attr = false;
-                if (!tma_attr) {
-                    B2_CUDA_CHECK(cudaFuncSetAttribute(vi_sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                    tma_attr = true;
-                }
+                B2_CUDA_CHECK(cudaFuncSetAttribute(vi_sweep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                 g.tile_states = ts;
                 const int64_t n_tiles = (g.rows + ts - 1) / ts;
                 const int64_t sms = sm_count();
@@ -475,11 +471,8 @@ extern "C" int b2_vi_sweep(const b2_vi_problem* p, const double* v_in, const dou
     if (tile < 1) tile = 1;
     g.tile_states = tile;
     const size_t smem = ((size_t)tile * E + (size_t)tile * g.A) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        B2_CUDA_CHECK(cudaFuncSetAttribute(vi_sweep_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
+    // per device and cheap: set on every call (a process may drive several devices)
+    B2_CUDA_CHECK(cudaFuncSetAttribute(vi_sweep_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     const int64_t n_tiles = (g.rows + tile - 1) / tile;
     const int64_t max_grid = (int64_t)sm_count() * 8;
     const unsigned grid = (unsigned)(n_tiles < max_grid ? n_tiles : max_grid);
