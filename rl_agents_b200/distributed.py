@@ -3,6 +3,11 @@
 
   OPD / batched decisions   independent trees are sharded over ranks; no
                             data-path collective (results gathered at the end).
+  OPD / one big decision    sub-tree sharding (ShardedOPD): every rank expands the
+                            root identically to depth k, the depth-k sub-trees are
+                            dealt round-robin, each rank searches its sub-trees
+                            best-first, and ONE all-reduce(max) of the sub-trees'
+                            (value_lower, value_upper) decides the action.
   MCTS root parallelism     every rank grows its own tree on episodes/world
                             episodes from the same root with an independent RNG
                             stream; ONE all-reduce of the root's per-action
@@ -99,3 +104,107 @@ def recommend(counts, values):
     values = np.asarray(values)
     ties = np.nonzero(counts == counts.max())[0]
     return int(max(ties, key=lambda i: values[i]))
+
+
+class ShardedOPD(object):
+    """One OPD decision on HighwayLite sharded over the ranks of a process group (SURVEY 8e,
+    BASELINE config C5's "tree-sharded"): best-first order is global in the reference, so an exact
+    shard would need an arg-max exchange per expansion; instead the top of the tree is replicated.
+
+      1. every rank expands the root to depth k (smallest k with #sub-trees >= world, k <= 3)
+         with the batched transition kernel -- identical on all ranks;
+      2. sub-tree j goes to rank j % world and gets an equal share of the remaining budget;
+         each rank runs its sub-trees as one batch on the OPD engine (strict best-first inside
+         each sub-tree);
+      3. one all_reduce(MAX) of the [n_subtrees, 2] (lower, upper) table;
+      4. every rank backs the replicated top levels up (max over children, deterministic.py:74-79)
+         and returns the arg-max value_lower root action.
+
+    The node set differs from a single best-first tree of the same budget (the budget is split
+    evenly instead of greedily); with world == 1 the same decomposition runs on one GPU, which is
+    what the parity test compares against."""
+
+    def __init__(self, budget, gamma, terminal_reward=0.0, group=None, device="cuda", max_depth=3):
+        self.budget, self.gamma, self.terminal_reward = int(budget), float(gamma), float(terminal_reward)
+        self.group, self.device, self.max_depth = group, device, max_depth
+
+    def _world(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group), dist.get_rank(self.group)
+        return 1, 0
+
+    def _expand_level(self, words_list, actions_list):
+        """Batched env transition of (scene, action) pairs on the device."""
+        import torch
+        from rl_agents_b200 import _lib
+        lib = _lib.load()
+        n = len(words_list)
+        st = torch.tensor(np.stack(words_list), dtype=torch.int32, device=self.device)
+        act = torch.tensor(actions_list, dtype=torch.int32, device=self.device)
+        rew = torch.empty(n, dtype=torch.float32, device=self.device)
+        flg = torch.empty(n, dtype=torch.int32, device=self.device)
+        _lib.check(lib.b2_highway_step(_lib.ptr(st), _lib.ptr(act), _lib.ptr(rew), _lib.ptr(flg), None, n,
+                                       _lib.current_stream()))
+        return st.cpu().numpy(), rew.cpu().numpy().astype(np.float64), (flg.cpu().numpy() & 1).astype(bool)
+
+    def decide(self, root_words):
+        import torch
+        from rl_agents_b200 import _lib
+        from rl_agents_b200.engine.opd import OPDEngine
+        from rl_agents_b200.envs.highway_lite import available_actions
+        world, rank = self._world()
+        g = self.gamma
+        # top of the tree, replicated: nodes = dicts in creation order
+        top = [dict(parent=-1, action=-1, depth=0, words=np.asarray(root_words, dtype=np.int32), lower=0.0,
+                    done=False, children=[])]
+        frontier, spent, depth = [0], 0, 0
+        while depth < self.max_depth and (depth == 0 or len(frontier) < world):
+            pairs = [(i, a) for i in frontier if not top[i]["done"] for a in available_actions(top[i]["words"])]
+            if not pairs:
+                break
+            words, rew, term = self._expand_level([top[i]["words"] for i, _ in pairs], [a for _, a in pairs])
+            depth += 1
+            new_frontier = []
+            for (i, a), w, r, t in zip(pairs, words, rew, term):
+                lower = top[i]["lower"] + (g ** (depth - 1)) * r           # deterministic.py:52
+                if t:
+                    lower = lower + self.terminal_reward * (g ** depth) / (1 - g)
+                top.append(dict(parent=i, action=a, depth=depth, words=w, lower=lower, done=bool(t), children=[]))
+                top[i]["children"].append(len(top) - 1)
+                new_frontier.append(len(top) - 1)
+            spent += len(pairs)
+            frontier = new_frontier + [i for i in frontier if top[i]["done"]]
+        subtrees = [i for i in frontier if not top[i]["done"] and not top[i]["children"]]
+        table = torch.full((max(len(subtrees), 1), 2), -np.inf, dtype=torch.float64, device=self.device)
+        mine = [j for j in range(len(subtrees)) if j % world == rank]
+        per_tree = max((self.budget - spent) // max(len(subtrees), 1), 5)
+        if mine:
+            eng = OPDEngine(_lib.ENV_HIGHWAY, len(mine), 5, per_tree, g, self.terminal_reward, device=self.device,
+                            keys_in_smem=True)
+            eng.plan(torch.tensor(np.stack([top[subtrees[j]]["words"] for j in mine]), dtype=torch.int32,
+                                  device=self.device))
+            eng.finish()
+            for slot, j in enumerate(mine):
+                node = top[subtrees[j]]
+                scale = g ** node["depth"]
+                table[j, 0] = node["lower"] + scale * float(eng.lower[slot, 0].item())
+                table[j, 1] = node["lower"] + scale * float(eng.upper[slot, 0].item())
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(table, op=dist.ReduceOp.MAX, group=self.group)      # the single exchange step
+        table = table.cpu().numpy()
+        # back the replicated levels up
+        lo = {i: n["lower"] for i, n in enumerate(top)}
+        up = {i: n["lower"] + (0.0 if n["done"] else (g ** n["depth"]) / (1 - g)) for i, n in enumerate(top)}
+        for j, i in enumerate(subtrees):
+            lo[i], up[i] = float(table[j, 0]), float(table[j, 1])
+        for i in range(len(top) - 1, -1, -1):
+            if top[i]["children"]:
+                lo[i] = max(lo[c] for c in top[i]["children"])
+                up[i] = max(up[c] for c in top[i]["children"])
+        kids = top[0]["children"]
+        best = max(kids, key=lambda c: lo[c])          # first max: ties resolved towards the earliest child
+        return dict(action=top[best]["action"], root_lower=lo[0], root_upper=up[0],
+                    children={top[c]["action"]: (lo[c], up[c]) for c in kids}, n_subtrees=len(subtrees),
+                    budget_per_subtree=per_tree, table=table)

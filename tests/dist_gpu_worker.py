@@ -51,6 +51,12 @@ def main():
     mc, mv = merge_root_statistics(counts, values)
     out["mcts_total"] = float(mc.sum().item())
     out["mcts_action"] = recommend(mc.cpu().numpy(), mv.cpu().numpy())
+    # --- sub-tree sharded OPD: one all-reduce(max); must equal the same decomposition run on one GPU ---
+    from rl_agents_b200.distributed import ShardedOPD
+    sharded = ShardedOPD(3000, 0.85, device=dev).decide(oenvs.make_highway_state(5).pack())
+    out["sharded_action"] = int(sharded["action"])
+    out["sharded_children"] = {str(k): list(v) for k, v in sharded["children"].items()}
+    out["sharded_root"] = [sharded["root_lower"], sharded["root_upper"], sharded["n_subtrees"]]
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:

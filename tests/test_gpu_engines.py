@@ -296,7 +296,7 @@ def run_opd_highway(words_list, budget, gamma, keys_in_smem=False, kernel=0):
 
 
 @pytest.mark.parametrize("key,smem", [("s0_b75_g0.7", False), ("s1_b300_g0.8", False), ("s1_b300_g0.8", True),
-                                      ("s2_b1000_g0.8", False)])
+                                      ("s2_b1000_g0.8", False), ("s0_b10000_g0.8", True), ("s0_b10000_g0.8", False)])
 def test_opd_highway_golden(key, smem):
     g = H["opd"][key]
     words = np.array(H["states"][key[1]], dtype=np.int32)
@@ -457,3 +457,55 @@ def test_olop_default_hoeffding_is_degenerate_like_the_reference():
                                  100, 0.8, rng, upper_bound=ub, continuation_type="zeros")
     assert plans[0] == plan == [0] * 6
     assert eng.tree_dict(0)["count"].tolist() == t.count
+
+
+# ------------------------------------------------- BASELINE full sizes ----
+def test_vi_full_size_c4_vs_numpy():
+    """C4 shape (S = 1e6, A = 8, B = 4 sparse): three sweeps against numpy, bit for bit, plus the
+    fixed-point property V_{k+1} = max_a Q_{k+1} and the contraction |Q_{k+1} - Q_k| <= gamma^k max R."""
+    import torch
+    from rl_agents_b200.engine.vi import VIEngine
+    S, A, B, gamma = 1_000_000, 8, 4, 0.95
+    P, N, R = oenvs.garnet(S, A, B, seed=0)
+    term = np.zeros(S, bool)
+    eng = VIEngine("sparse", P, R, term, nxt=N, gamma=gamma)
+    eng.reset(3)
+    q_prev = np.zeros((S, A))
+    v = np.zeros(S)
+    for k in range(3):
+        eng.sweep(k)
+        q_ref = planners.bellman_expectation("sparse", P, R, term, v, gamma, nxt=N)
+        q = eng.q[(k + 1) & 1].cpu().numpy()
+        assert np.array_equal(q, q_ref), k
+        v = q_ref.max(axis=-1)
+        assert np.array_equal(eng.v[(k + 1) & 1].cpu().numpy(), v)
+        assert np.abs(q - q_prev).max() <= gamma ** k * R.max() + 1e-12
+        q_prev = q
+    assert (eng.viol.cpu().numpy() > 0).all()
+
+
+def test_mcts_full_size_c3_invariants():
+    """C3 shape (4096 episodes x horizon 20 on HighwayLite) is beyond the Python oracle's reach
+    (81 920 env steps per decision): size-independent properties instead."""
+    from rl_agents_b200 import _lib
+    seeds = [70, 71, 72, 73, 74]
+    words = [oenvs.make_highway_state(s).pack() for s in seeds]
+    eng, plans, res, rng_words, gens = run_mcts(_lib.ENV_HIGHWAY, words, 4096, 20, 0.8, 10.0, [1, 2, 3, 4, 5])
+    vmax = (1 - 0.8 ** 20) / (1 - 0.8)
+    for i in range(len(seeds)):
+        d = eng.tree_dict(i)
+        n = len(d["parent"])
+        assert d["count"][0] == 4096                                   # every episode backs up through the root
+        kids = d["first_child"] >= 0
+        for p in np.nonzero(kids)[0][:2000]:
+            c = slice(d["first_child"][p], d["first_child"][p] + d["n_children"][p])
+            assert d["count"][c].sum() <= d["count"][p]                 # a visit of a child is a visit of its parent
+            assert (d["parent"][c] == p).all()
+        assert (d["value"] >= 0).all() and (d["value"] <= vmax + 1e-9).all()
+        assert np.all(d["count"][1:] <= d["count"][d["parent"][1:]])
+        assert 1 <= len(plans[i]) <= 20 and res[i, 2] <= 4096 * 20
+        # the recommended first action is the most visited root child (mcts.py:212-218)
+        c = slice(d["first_child"][0], d["first_child"][0] + d["n_children"][0])
+        assert plans[i][0] == d["action"][c][np.argmax(d["count"][c])] or \
+            (d["count"][c] == d["count"][c].max()).sum() > 1
+    assert len({tuple(w) for w in rng_words.tolist()}) == len(seeds)   # independent streams advanced

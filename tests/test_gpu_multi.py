@@ -29,3 +29,33 @@ def test_two_rank_vi_and_root_parallel_mcts():
     # every episode of both trees counted once; the episode that expands a root descends into no child
     assert res[0]["mcts_total"] == res[1]["mcts_total"] == 64.0 - 2
     assert res[0]["mcts_action"] == res[1]["mcts_action"]
+    # sharded OPD: both ranks agree, and equal the single-GPU run of the same decomposition bit for bit
+    import torch
+    from oracle import envs as oenvs
+    from rl_agents_b200.distributed import ShardedOPD
+    assert res[0]["sharded_children"] == res[1]["sharded_children"] and res[0]["sharded_action"] == res[1]["sharded_action"]
+    torch.cuda.set_device(0)
+    single = ShardedOPD(3000, 0.85, device="cuda:0").decide(oenvs.make_highway_state(5).pack())
+    assert {str(k): list(v) for k, v in single["children"].items()} == res[0]["sharded_children"]
+    assert int(single["action"]) == res[0]["sharded_action"]
+    assert [single["root_lower"], single["root_upper"], single["n_subtrees"]] == res[0]["sharded_root"]
+
+
+def test_sharded_opd_single_rank_is_consistent_with_plain_opd():
+    """world == 1: the decomposition's bounds bracket / agree with a plain OPD search of the scene."""
+    import numpy as np
+    from oracle import envs as oenvs
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.distributed import ShardedOPD
+    from rl_agents_b200.engine.opd import OPDEngine
+    import torch
+    words = oenvs.make_highway_state(6).pack()
+    d = ShardedOPD(2000, 0.8, device="cuda").decide(words)
+    assert d["action"] in d["children"] and d["root_lower"] <= d["root_upper"]
+    eng = OPDEngine(_lib.ENV_HIGHWAY, 1, 5, 2000, 0.8)
+    eng.plan(torch.tensor(words, dtype=torch.int32, device="cuda").reshape(1, -1))
+    plans, _ = eng.finish([np.random.default_rng(0)])
+    lo, up = float(eng.lower[0, 0]), float(eng.upper[0, 0])
+    # both are valid brackets of the same optimal value: the intervals must intersect
+    assert max(lo, d["root_lower"]) <= min(up, d["root_upper"]) + 1e-12
+    assert plans[0][0] in d["children"]
