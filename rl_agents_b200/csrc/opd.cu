@@ -79,7 +79,7 @@ struct Tournament {
 };
 
 struct Shared {
-    int leaf, depth, n_avail, error, done_parent;
+    int leaf, depth, error, done_parent;
     double lower;
     int child_action[MAX_BRANCH];
     int child_done[MAX_BRANCH];
