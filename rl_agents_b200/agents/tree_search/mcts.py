@@ -41,12 +41,12 @@ class MCTS(AbstractPlanner):
         cfg.update({"temperature": 2 / (1 - cfg["gamma"]), "closed_loop": False})    # mcts.py:120-127
         return cfg
 
-    def _engine_for(self, d):
+    def _engine_for(self, d, replicas, episodes):
         from rl_agents_b200.engine.mcts import MCTSEngine
-        key = (d.kind, d.n_actions, self.config["episodes"], self.config["horizon"], self.config["gamma"],
+        key = (d.kind, d.n_actions, replicas, episodes, self.config["horizon"], self.config["gamma"],
                self.config["temperature"], id(d.mdp))
         if key != self._engine_key:
-            self.engine = MCTSEngine(d.kind, 1, d.n_actions, self.config["episodes"], self.config["horizon"],
+            self.engine = MCTSEngine(d.kind, replicas, d.n_actions, episodes, self.config["horizon"],
                                      self.config["gamma"], self.config["temperature"], mdp=d.mdp,
                                      rollout_policy=self.rollout_policy, prior_policy=self.prior_policy)
             self._engine_key = key
@@ -56,13 +56,44 @@ class MCTS(AbstractPlanner):
         import torch
         from rl_agents_b200.engine.mcts import pcg64_words, set_pcg64_words
         d = describe(state)
-        eng = self._engine_for(d)
-        root = torch.from_numpy(d.root.reshape(1, -1) if d.root.size > 1 else d.root).to(eng.device)
-        eng.plan(root.contiguous(), pcg64_words(self.np_random).reshape(1, -1))
-        plans, res, rng_words = eng.finish()
-        set_pcg64_words(self.np_random, rng_words[0])     # the device consumed the planner's stream
+        replicas = int(self.config.get("root_parallel", 1) or 1)
+        root = torch.from_numpy(d.root.reshape(1, -1) if d.root.size > 1 else d.root)
+        if replicas <= 1:
+            # the reference's semantics: one tree, strict episode order, the planner's own RNG stream
+            eng = self._engine_for(d, 1, self.config["episodes"])
+            eng.plan(root.to(eng.device).contiguous(), pcg64_words(self.np_random).reshape(1, -1))
+            plans, res, rng_words = eng.finish()
+            set_pcg64_words(self.np_random, rng_words[0])     # the device consumed the planner's stream
+            self.last_tree = eng
+            return plans[0]
+        # extension ("root_parallel": R): R independent trees of episodes/R episodes from the same root,
+        # each on its own spawned stream; root statistics merged as in rl_agents_b200.distributed
+        from rl_agents_b200.distributed import recommend
+        episodes = -(-int(self.config["episodes"]) // replicas)
+        eng = self._engine_for(d, replicas, episodes)
+        gens = self.np_random.spawn(replicas)
+        roots = root.repeat(replicas, 1) if d.root.size > 1 else root.repeat(replicas)
+        eng.plan(roots.to(eng.device).contiguous(), np.stack([pcg64_words(g) for g in gens]))
+        plans, res, _ = eng.finish()
         self.last_tree = eng
-        return plans[0]
+        fc = eng.first_child[:, 0].cpu().numpy()
+        counts = np.zeros(d.n_actions)
+        sums = np.zeros(d.n_actions)
+        per_replica = []
+        for t in range(replicas):
+            n = int((eng.meta[t, 0].item() >> 8) & 0xff)
+            acts = (eng.meta[t, fc[t]:fc[t] + n].cpu().numpy() & 0xff).astype(int)
+            c = eng.count[t, fc[t]:fc[t] + n].cpu().numpy().astype(float)
+            v = eng.value[t, fc[t]:fc[t] + n].cpu().numpy()
+            counts[acts] += c
+            sums[acts] += c * v
+            per_replica.append(dict(zip(acts.tolist(), c.tolist())))
+        values = np.where(counts > 0, sums / np.maximum(counts, 1), 0.0)
+        best = recommend(counts, values)
+        donor = max(range(replicas), key=lambda t: per_replica[t].get(best, 0.0))
+        tail = plans[donor][1:] if plans[donor] and plans[donor][0] == best else []
+        self.root_statistics = {"counts": counts, "values": values}
+        return [best] + tail
 
 
 @register_with_reference

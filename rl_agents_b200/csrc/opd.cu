@@ -326,8 +326,11 @@ __global__ void __launch_bounds__(HW_THREADS) opd_highway_kernel(OpdArgs a) {
 // slots do real work (a lone tree fills 3.8 of its 6 slots).  Node order inside
 // every tree is unchanged: the trees are independent, only the slots are shared.
 // ---------------------------------------------------------------------------
-constexpr int MT_TREES = 8;
-constexpr int MT_THREADS = 256;
+#ifndef B2_MT_TREES
+#define B2_MT_TREES 8
+#endif
+constexpr int MT_TREES = B2_MT_TREES;
+constexpr int MT_THREADS = 32 * MT_TREES;
 constexpr int MT_GROUPS = MT_THREADS / 16;
 
 struct MultiShared {

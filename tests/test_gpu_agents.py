@@ -119,3 +119,20 @@ def test_agents_reject_unsupported_envs_and_options():
         MCTSAgent(finite_env(), {"closed_loop": True})
     with pytest.raises(KeyError):
         MCTSAgent(finite_env(), {"horizon": 5}).plan(None)        # mcts.py:116-118,180: episodes missing
+
+
+def test_mcts_root_parallel_extension():
+    """"root_parallel": R (not in the reference): R trees of episodes/R from the same root, merged
+    root statistics.  Deterministic for a given planner seed; every episode is accounted for."""
+    from rl_agents_b200.agents.tree_search.mcts import MCTSAgent
+    from rl_agents_b200.envs import HighwayLiteEnv
+    cfg = {"episodes": 512, "horizon": 8, "gamma": 0.8, "root_parallel": 16}
+    plans = []
+    for _ in range(2):
+        agent = MCTSAgent(HighwayLiteEnv(seed=2), dict(cfg))
+        agent.seed(7)
+        plans.append(agent.plan(None))
+        stats = agent.planner.root_statistics
+        assert stats["counts"].sum() == 16 * (512 // 16 - 1)       # the expanding episode of each tree selects no child
+        assert plans[-1][0] == int(np.argmax(stats["counts"])) or (stats["counts"] == stats["counts"].max()).sum() > 1
+    assert plans[0] == plans[1]
