@@ -102,6 +102,14 @@ int b2_vi_sweep(const b2_vi_problem* p, const double* v_in, const double* q_old,
 int b2_vi_solve(const b2_vi_problem* p, double* q0, double* q1, double* v0, double* v1,
                 int32_t* viol, int32_t iterations, void* stream);
 
+/* Robust value iteration (rl_agents/agents/dynamic_programming/robust_value_iteration.py:39-58):
+ * Q' = min over n_models models of R_m + gamma * E_m[V(s')], no terminal handling.
+ * p->transition: int32 [M,S,A] (deterministic) or double [M,S,A,S] (stochastic);
+ * p->reward: double [M,S,A]; p->terminal / p->next unused; rows = all states.
+ * Same viol / early-exit protocol as b2_vi_sweep. */
+int b2_vi_robust_sweep(const b2_vi_problem* p, int32_t n_models, const double* v_in, const double* q_old,
+                       double* q_new, double* v_out, int32_t* viol, int32_t sweep_index, void* stream);
+
 /* ------------------------------------------------------------------------
  * OPD -- rl_agents/agents/tree_search/deterministic.py
  * A batch of n_trees independent decisions, one tree per CTA, strict

@@ -404,3 +404,25 @@ def value_iteration(mode, transition, reward, terminal, gamma, iterations, nxt=N
             break
         q = nq
     return q, sweeps
+
+
+def robust_value_iteration(mode, transitions, rewards, gamma, iterations):
+    """RobustValueIterationAgent.get_state_action_value (robust_value_iteration.py:39-58):
+    Q <- min over the M models of R_m + gamma * E_m[max_a Q]; no terminal handling; the
+    fixed-point loop and its allclose early exit are ValueIterationAgent's (:65-73)."""
+    q = np.zeros(transitions.shape[1:3])
+    sweeps = 0
+    for _ in range(iterations):
+        sweeps += 1
+        value = q.max(axis=-1)
+        if mode == "deterministic":
+            next_v = value[transitions]
+        elif mode == "stochastic":
+            next_v = (transitions * value.reshape((1, 1, 1, np.size(value)))).sum(axis=-1)
+        else:
+            raise ValueError("Unknown mode")
+        nq = np.min(rewards + gamma * next_v, axis=0)
+        if np.allclose(q, nq):
+            break
+        q = nq
+    return q, sweeps

@@ -74,6 +74,7 @@ EXPORTS = {
     "b2_highway_step": (c_int, [c_void_p] * 5 + [c_int32, c_void_p]),
     "b2_vi_sweep": (c_int, [ctypes.POINTER(VIProblem)] + [c_void_p] * 5 + [c_int32, c_void_p]),
     "b2_vi_solve": (c_int, [ctypes.POINTER(VIProblem)] + [c_void_p] * 5 + [c_int32, c_void_p]),
+    "b2_vi_robust_sweep": (c_int, [ctypes.POINTER(VIProblem), c_int32] + [c_void_p] * 5 + [c_int32, c_void_p]),
     "b2_opd_workspace_bytes": (c_int64, [ctypes.POINTER(OPDConfig)]),
     "b2_opd_plan": (c_int, [ctypes.POINTER(OPDConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
                             c_void_p, c_void_p]),

@@ -382,6 +382,43 @@ __global__ void vi_rowmax_kernel(SweepArgs g) {
     g.v_out[g.row_begin + s] = m;
 }
 
+// ---------------------------------------------------------------------------
+// Robust value iteration (robust_value_iteration.py:39-58): Q' = min over the M
+// models of R_m + gamma * E_m[V(s')]; no terminal handling.  One thread per (s,a)
+// loops over the models (deterministic: one gather each; stochastic: a dense
+// row in numpy's summation order); V' = max_a Q' by vi_rowmax_kernel.
+// ---------------------------------------------------------------------------
+struct RobustArgs {
+    const void* transition;   // int32 [M, S, A]  |  double [M, S, A, S]
+    const double* reward;     // [M, S, A]
+    int n_models, dense;
+};
+
+__global__ void __launch_bounds__(128) vi_robust_kernel(SweepArgs g, RobustArgs ra) {
+    if (g.sweep > 0 && g.viol[g.sweep - 1] == 0) return;
+    const int64_t n_rows = g.rows * g.A;
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    int bad = 0;
+    if (row < n_rows) {
+        double q = INFINITY;
+        for (int m = 0; m < ra.n_models; ++m) {
+            double nv;
+            if (ra.dense) {
+                const double* p = (const double*)ra.transition + ((int64_t)m * n_rows + row) * g.rows;
+                nv = np_pairwise_sum([&](int i) { return p[i] * g.v_in[i]; }, 0, (int)g.rows);
+            } else {
+                nv = g.v_in[((const int32_t*)ra.transition)[(int64_t)m * n_rows + row]];
+            }
+            const double qm = ra.reward[(int64_t)m * n_rows + row] + g.gamma * nv;
+            q = qm < q ? qm : q;                       // np.min over the model axis
+        }
+        if (!np_isclose(g.q_old[row], q, g.rtol, g.atol)) bad = 1;
+        g.q_new[row] = q;
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(g.viol + g.sweep, bad);
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -490,5 +527,24 @@ extern "C" int b2_vi_solve(const b2_vi_problem* p, double* q0, double* q1, doubl
         int rc = b2_vi_sweep(p, v[k & 1], q[k & 1], q[(k + 1) & 1], v[(k + 1) & 1], viol, k, stream);
         if (rc) return rc;
     }
+    return B2_OK;
+}
+
+extern "C" int b2_vi_robust_sweep(const b2_vi_problem* p, int32_t n_models, const double* v_in, const double* q_old,
+                                  double* q_new, double* v_out, int32_t* viol, int32_t sweep_index, void* stream_) {
+    B2_REQUIRE(p && v_in && q_old && q_new && v_out && viol && p->transition && p->reward, "null pointer");
+    B2_REQUIRE(n_models > 0 && p->n_actions > 0 && p->row_begin == 0 && p->row_end == p->n_states, "bad shape");
+    B2_REQUIRE(p->mode == B2_VI_DETERMINISTIC || p->mode == B2_VI_STOCHASTIC, "robust VI: deterministic or stochastic mode");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SweepArgs g;
+    memset(&g, 0, sizeof(g));
+    g.v_in = v_in; g.q_old = q_old; g.q_new = q_new; g.v_out = v_out; g.viol = viol; g.sweep = sweep_index;
+    g.rows = p->n_states; g.row_begin = 0; g.A = p->n_actions; g.gamma = p->gamma; g.rtol = p->rtol; g.atol = p->atol;
+    RobustArgs ra;
+    ra.transition = p->transition; ra.reward = p->reward; ra.n_models = n_models; ra.dense = p->mode == B2_VI_STOCHASTIC;
+    const int64_t n_rows = g.rows * g.A;
+    vi_robust_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, stream>>>(g, ra);
+    vi_rowmax_kernel<<<(unsigned)((g.rows + 255) / 256), 256, 0, stream>>>(g);
+    B2_CUDA_CHECK(cudaGetLastError());
     return B2_OK;
 }

@@ -81,3 +81,43 @@ class VIEngine(object):
             k = int(zero[0])
             return self.q[k & 1], k + 1
         return self.q[iterations & 1], int(iterations)
+
+
+class RobustVIEngine(object):
+    """Device side of RobustValueIterationAgent: M models, Q <- min_m (R_m + gamma E_m[max_a Q])."""
+
+    def __init__(self, mode, transitions, rewards, gamma=1.0, device="cuda", rtol=1e-5, atol=1e-8):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        rewards = np.asarray(rewards, dtype=np.float64)
+        self.n_models, self.n_states, self.n_actions = rewards.shape
+        if mode == "deterministic":
+            self.transition = torch.as_tensor(np.ascontiguousarray(transitions, dtype=np.int32), device=self.device)
+        elif mode == "stochastic":
+            self.transition = torch.as_tensor(np.ascontiguousarray(transitions, dtype=np.float64), device=self.device)
+        else:
+            raise ValueError("Unknown mode")
+        self.reward = torch.as_tensor(np.ascontiguousarray(rewards), device=self.device)
+        self.problem = _lib.VIProblem(MODES[mode], self.n_actions, self.n_states, 0, self.n_states, 0, self.n_states,
+                                      float(gamma), rtol, atol, self.transition.data_ptr(), None,
+                                      self.reward.data_ptr(), None)
+        self.q = [torch.zeros(self.n_states, self.n_actions, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.v = [torch.zeros(self.n_states, dtype=torch.float64, device=self.device) for _ in range(2)]
+
+    def solve(self, iterations):
+        for t in self.q + self.v:
+            t.zero_()
+        self.viol = self.torch.zeros(max(int(iterations), 1), dtype=self.torch.int32, device=self.device)
+        for k in range(int(iterations)):
+            _lib.check(self.lib.b2_vi_robust_sweep(self.problem, self.n_models, _lib.ptr(self.v[k & 1]),
+                                                   _lib.ptr(self.q[k & 1]), _lib.ptr(self.q[(k + 1) & 1]),
+                                                   _lib.ptr(self.v[(k + 1) & 1]), _lib.ptr(self.viol), k,
+                                                   _lib.current_stream()))
+        viol = self.viol[:iterations].cpu().numpy()
+        zero = np.nonzero(viol == 0)[0]
+        if zero.size:
+            k = int(zero[0])
+            return self.q[k & 1], k + 1
+        return self.q[iterations & 1], int(iterations)

@@ -179,6 +179,24 @@ def main():
     vi["sparse_garnet500_g0.95_it100"] = run_vi(env_s, 0.95, 100)
     out["vi"] = vi
 
+    # ---------------- robust VI ----------------
+    from rl_agents.agents.dynamic_programming.robust_value_iteration import RobustValueIterationAgent
+    rvi = {}
+    models_det = []
+    for m in range(3):
+        Tm, Rm = envs.garnet(300, 4, 1, seed=20 + m, deterministic=True)
+        models_det.append({"mode": "deterministic", "transition": Tm.tolist(), "reward": Rm.tolist()})
+    agent = RobustValueIterationAgent(None, {"gamma": 0.9, "iterations": 60, "models": models_det})
+    rvi["det_3x300x4_g0.9_it60"] = {"q": agent.get_state_action_value().tolist(), "act7": int(agent.act(7))}
+    models_dense = []
+    for m in range(2):
+        rng_m = np.random.default_rng(30 + m)
+        Pm = rng_m.uniform(size=(40, 3, 40)); Pm /= Pm.sum(-1, keepdims=True)
+        models_dense.append({"mode": "stochastic", "transition": Pm.tolist(), "reward": rng_m.uniform(size=(40, 3)).tolist()})
+    agent = RobustValueIterationAgent(None, {"gamma": 0.95, "iterations": 100, "models": models_dense})
+    rvi["dense_2x40x3_g0.95_it100"] = {"q": agent.get_state_action_value().tolist(), "act7": int(agent.act(7))}
+    out["robust_vi"] = rvi
+
     # ---------------- OPD on finite ----------------
     opd = {}
     opd["large1_b500_g0.9"] = run_opd(finite(), 500, 0.9)

@@ -136,3 +136,19 @@ def test_mcts_root_parallel_extension():
         assert stats["counts"].sum() == 16 * (512 // 16 - 1)       # the expanding episode of each tree selects no child
         assert plans[-1][0] == int(np.argmax(stats["counts"])) or (stats["counts"] == stats["counts"].max()).sum() > 1
     assert plans[0] == plans[1]
+
+
+def test_robust_value_iteration_agent_matches_reference():
+    from rl_agents_b200.agents.dynamic_programming.robust_value_iteration import RobustValueIterationAgent
+    from tests.test_oracle import robust_models
+    for key, kind, gamma, it in [("det_3x300x4_g0.9_it60", "det", 0.9, 60), ("dense_2x40x3_g0.95_it100", "dense", 0.95, 100)]:
+        mode, T, R = robust_models(kind)
+        models = [{"mode": mode, "transition": T[m].tolist(), "reward": R[m].tolist()} for m in range(len(T))]
+        agent = RobustValueIterationAgent(None, {"gamma": gamma, "iterations": it, "models": models})
+        q = agent.get_state_action_value()
+        assert np.array_equal(q, np.array(G["robust_vi"][key]["q"])), key
+        assert agent.act(7) == G["robust_vi"][key]["act7"]
+        q_ref, sweeps = planners.robust_value_iteration(mode, T, R, gamma, it)
+        assert agent.sweeps == sweeps
+    with pytest.raises(ValueError):
+        RobustValueIterationAgent(None, {})

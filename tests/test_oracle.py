@@ -118,6 +118,28 @@ def test_value_iteration():
     assert np.array_equal(q, np.array(G["vi"]["sparse_garnet500_g0.95_it100"]["q"]))
 
 
+def robust_models(kind):
+    if kind == "det":
+        ms = [envs.garnet(300, 4, 1, seed=20 + m, deterministic=True) for m in range(3)]
+        return "deterministic", np.array([m[0] for m in ms]), np.array([m[1] for m in ms])
+    Ps, Rs = [], []
+    for m in range(2):
+        rng = np.random.default_rng(30 + m)
+        P = rng.uniform(size=(40, 3, 40))
+        P /= P.sum(-1, keepdims=True)
+        Ps.append(P)
+        Rs.append(rng.uniform(size=(40, 3)))
+    return "stochastic", np.array(Ps), np.array(Rs)
+
+
+def test_robust_value_iteration():
+    for key, kind, gamma, it in [("det_3x300x4_g0.9_it60", "det", 0.9, 60), ("dense_2x40x3_g0.95_it100", "dense", 0.95, 100)]:
+        mode, T, R = robust_models(kind)
+        q, _ = planners.robust_value_iteration(mode, T, R, gamma, it)
+        assert np.array_equal(q, np.array(G["robust_vi"][key]["q"])), key
+        assert int(np.argmax(q[7])) == G["robust_vi"][key]["act7"]
+
+
 # ------------------------- HighwayLite -------------------------
 def test_highway_scene_and_traces_are_reproducible():
     for seed, words in H["states"].items():
