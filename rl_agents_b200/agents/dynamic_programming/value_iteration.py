@@ -1,88 +1,105 @@
-"""Value-iteration agent on the device engine.  Drop-in for
-rl_agents.agents.dynamic_programming.value_iteration.ValueIterationAgent
-(value_iteration.py:9-111)."""
+"""Value-iteration agent on the device engine.
+
+Drop-in for the reference's ValueIterationAgent
+(rl_agents/agents/dynamic_programming/value_iteration.py:9-111): the constructor
+solves the MDP once, `act` is an arg-max over the state's row of Q.  The fixed
+point iteration itself (Bellman operator, max over actions, allclose early exit
+that returns the previous iterate) runs in `b2_vi_solve`; nothing is iterated on
+the host.
+"""
 import numpy as np
 
 from rl_agents_b200.agents.common.abstract import AbstractAgent, register_with_reference
+
+_NOT_AN_MDP = ("Environment must be of type finite_mdp.envs.finite_mdp.FiniteMDPEnv or handle a "
+               "conversion method called 'to_finite_mdp' to such a type.")
+
+
+def _third_party_finite_mdp_env():
+    """The `finite_mdp` package's env class when it is installed, else None."""
+    try:
+        return __import__("finite_mdp.envs.finite_mdp_env").envs.finite_mdp_env.FiniteMDPEnv
+    except (ModuleNotFoundError, AttributeError, TypeError):
+        return None
 
 
 @register_with_reference
 class ValueIterationAgent(AbstractAgent):
     def __init__(self, env, config=None):
         super(ValueIterationAgent, self).__init__(config)
-        self.finite_mdp = self.is_finite_mdp(env)
-        if self.finite_mdp:
-            self.mdp = env.unwrapped.mdp
-        else:
-            try:
-                self.mdp = env.unwrapped.to_finite_mdp()
-            except AttributeError:
-                raise TypeError("Environment must be of type finite_mdp.envs.finite_mdp.FiniteMDPEnv or handle a "
-                                "conversion method called 'to_finite_mdp' to such a type.")
         self.env = env
-        self.sweeps = 0
+        self.finite_mdp = self.is_finite_mdp(env)
+        self.mdp = self._current_mdp()
+        self.sweeps = 0                      # sweeps the last solve performed (diagnostics)
         self.state_action_value = self.get_state_action_value()
 
     @classmethod
     def default_config(cls):
-        return dict(gamma=1.0, iterations=100)
+        return {"gamma": 1.0, "iterations": 100}       # value_iteration.py:24-27
 
-    def act(self, state):
-        if not self.finite_mdp:                       # value_iteration.py:31-34: re-solve on every act
-            self.mdp = self.env.unwrapped.to_finite_mdp()
-            state = self.mdp.state
-            self.state_action_value = self.get_state_action_value()
-        return np.argmax(self.state_action_value[state, :])
+    # -- MDP hand-off ---------------------------------------------------------
+    @staticmethod
+    def is_finite_mdp(env):
+        unwrapped = getattr(env, "unwrapped", env)
+        if getattr(unwrapped, "b2_env_kind", None) == "finite":
+            return True
+        third_party = _third_party_finite_mdp_env()
+        return third_party is not None and isinstance(unwrapped, third_party)
 
+    def _current_mdp(self):
+        if self.finite_mdp:
+            return self.env.unwrapped.mdp
+        converter = getattr(self.env.unwrapped, "to_finite_mdp", None)
+        if converter is None:
+            raise TypeError(_NOT_AN_MDP)
+        return converter()
+
+    # -- solving ----------------------------------------------------------------
     def get_state_action_value(self):
-        """fixed_point_iteration on Q (value_iteration.py:42-45,65-73) by b2_vi_solve."""
+        """Q of shape [S, A] (numpy, host copy of the device result)."""
         from rl_agents_b200.engine.vi import VIEngine
-        m = self.mdp
-        eng = VIEngine(m.mode, m.transition, m.reward, m.terminal, nxt=getattr(m, "next", None),
-                       gamma=self.config["gamma"])
-        q, self.sweeps = eng.solve(self.config["iterations"])
+        mdp = self.mdp
+        engine = VIEngine(mdp.mode, mdp.transition, mdp.reward, mdp.terminal, nxt=getattr(mdp, "next", None),
+                          gamma=self.config["gamma"])
+        q, self.sweeps = engine.solve(self.config["iterations"])
         return q.cpu().numpy()
 
     def get_state_value(self):
-        return self.state_action_value.max(axis=-1)
+        return self.best_action_value(self.state_action_value)
 
     @staticmethod
     def best_action_value(action_values):
         return action_values.max(axis=-1)
 
-    @staticmethod
-    def is_finite_mdp(env):
-        u = getattr(env, "unwrapped", env)
-        if getattr(u, "b2_env_kind", None) == "finite":
-            return True
-        try:
-            finite_mdp = __import__("finite_mdp.envs.finite_mdp_env")
-            return isinstance(u, finite_mdp.envs.finite_mdp_env.FiniteMDPEnv)
-        except (ModuleNotFoundError, TypeError):
-            return False
+    # -- acting -----------------------------------------------------------------
+    def act(self, state):
+        if not self.finite_mdp:
+            # envs that are only convertible are re-converted and re-solved at every decision (:31-34)
+            self.mdp = self._current_mdp()
+            self.state_action_value = self.get_state_action_value()
+            state = self.mdp.state
+        return np.argmax(self.state_action_value[state, :])
 
     def plan_trajectory(self, state, horizon=10):
-        action_value = self.state_action_value
+        """Greedy roll-out of the solved policy through the (deterministic) transition table."""
         states, actions = [], []
         for _ in range(horizon):
-            action = np.argmax(action_value[state])
             states.append(state)
-            actions.append(action)
-            state = self.mdp.next_state(state, action)
+            actions.append(np.argmax(self.state_action_value[state]))
+            state = self.mdp.next_state(state, actions[-1])
             if self.mdp.terminal[state]:
-                states.append(state)
-                actions.append(None)
-                break
+                return states + [state], actions + [None]
         return states, actions
 
+    # -- nothing to learn, nothing to checkpoint ----------------------------------
     def record(self, state, action, reward, next_state, done, info):
-        pass
+        return None
 
     def reset(self):
-        pass
+        return None
 
     def seed(self, seed=None):
-        pass
+        return None
 
     def save(self, filename):
         return False
