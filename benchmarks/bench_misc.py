@@ -52,6 +52,11 @@ def main():
     w1 = pcg64_words(gen).reshape(1, -1)
     out["mcts_highway_4096x20_single_decision_ms"] = timed(lambda: (meng.plan(scene, w1), meng.finish()), reps=3)
 
+    rp = MCTSEngine(_lib.ENV_HIGHWAY, 64, 5, 64, 20, 0.8, 10.0)            # root_parallel = 64: 64 trees x 64 episodes
+    scenes64 = scene.repeat(64, 1).contiguous()
+    w64 = np.stack([pcg64_words(g) for g in gen.spawn(64)])
+    out["mcts_highway_4096x20_root_parallel64_ms"] = timed(lambda: (rp.plan(scenes64, w64), rp.finish()), reps=3)
+
     # --- batches ---
     n = 148 * 256
     roots = torch.randint(0, 100, (n,), dtype=torch.int32, device=dev)
