@@ -509,3 +509,36 @@ def test_mcts_full_size_c3_invariants():
         assert plans[i][0] == d["action"][c][np.argmax(d["count"][c])] or \
             (d["count"][c] == d["count"][c].max()).sum() > 1
     assert len({tuple(w) for w in rng_words.tolist()}) == len(seeds)   # independent streams advanced
+
+
+# ------------------------------------------------------------ edge cases ----
+def test_edge_cases_small_budgets_and_argument_validation():
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.mcts import MCTSEngine, pcg64_words
+    from rl_agents_b200.engine.opd import OPDEngine
+    # budget < action_space.n: zero expansions, empty plan (the reference's get_plan returns [] too)
+    eng, plans, res = run_opd_finite(product_mdp(), 3, 0.9, [0, 1, 2])
+    assert plans == [[], [], []] and res[:, 0].tolist() == [1, 1, 1] and eng.tree_dict(0)["count"].tolist() == [1]
+    plan, t = planners.opd_plan(oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"]), 3, 0.9,
+                                np_random=np_random(0))
+    assert plan == [] and t.count == [1]
+    # exactly one expansion
+    eng, plans, res = run_opd_highway([oenvs.make_highway_state(0).pack()], 5, 0.8)
+    plan, t = planners.opd_plan(oenvs.HighwayLite(seed=0), 5, 0.8, np_random=np_random(0))
+    assert plans[0] == plan and eng.tree_dict(0)["count"].tolist() == t.count
+    # a single MCTS episode: expands the root, one rollout, no child visited
+    words = oenvs.make_highway_state(1).pack()
+    eng, plans, res, _, _ = run_mcts(_lib.ENV_HIGHWAY, [words], 1, 3, 0.8, 10.0, [4])
+    plan, t = planners.mcts_plan(oenvs.HighwayLite(seed=1), 1, 3, 0.8, 10.0, np_random(4))
+    assert plans[0] == plan and eng.tree_dict(0)["count"].tolist() == t.count
+    assert np.array_equal(eng.tree_dict(0)["value"], np.array(t.value))
+    # argument validation comes back as an error code + message, not a crash
+    bad = OPDEngine(_lib.ENV_FINITE, 1, 5, 100, 0.9, mdp=product_mdp())
+    bad.cfg.node_capacity = 3
+    with pytest.raises(_lib.B2Error, match="node_capacity"):
+        bad.plan(torch.zeros(1, dtype=torch.int32, device="cuda"))
+    m = MCTSEngine(_lib.ENV_FINITE, 1, 5, 4, 3, 0.9, 10.0, mdp=product_mdp())
+    m.cfg.rollout_policy = 7
+    with pytest.raises(_lib.B2Error, match="policy"):
+        m.plan(torch.zeros(1, dtype=torch.int32, device="cuda"), pcg64_words(np_random(0)).reshape(1, -1))
