@@ -57,6 +57,20 @@ def main():
     w64 = np.stack([pcg64_words(g) for g in gen.spawn(64)])
     out["mcts_highway_4096x20_root_parallel64_ms"] = timed(lambda: (rp.plan(scenes64, w64), rp.finish()), reps=3)
 
+    # --- C5-sized single decision: budget 1e6 (200 000 expansions), strict single tree and sub-tree sharded ---
+    if "--big" in sys.argv:
+        big = OPDEngine(_lib.ENV_HIGHWAY, 1, 5, 1_000_000, 0.9)
+        out["opd_highway_b1e6_single_tree_ms"] = timed(lambda: (big.plan(scene), big.finish([gen])), reps=1)
+        out["opd_highway_b1e6_max_depth"] = int(big.result[0, 2].item())
+        del big
+        from rl_agents_b200.distributed import ShardedOPD
+        sh = ShardedOPD(1_000_000, 0.9, device=dev)
+        t0 = time.perf_counter()
+        d = sh.decide(make_scene(0))
+        torch.cuda.synchronize()
+        out["opd_highway_b1e6_sharded_1gpu_ms"] = (time.perf_counter() - t0) * 1e3
+        out["opd_highway_b1e6_sharded_subtrees"] = d["n_subtrees"]
+
     # --- batches ---
     n = 148 * 256
     roots = torch.randint(0, 100, (n,), dtype=torch.int32, device=dev)
