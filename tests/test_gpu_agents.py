@@ -152,3 +152,30 @@ def test_robust_value_iteration_agent_matches_reference():
         assert agent.sweeps == sweeps
     with pytest.raises(ValueError):
         RobustValueIterationAgent(None, {})
+
+
+def test_batched_evaluation_equals_per_episode_agents():
+    """The lock-step batched episode runner takes the same actions, rewards and lengths as driving
+    one DeterministicPlannerAgent per episode (which itself equals the reference's plans)."""
+    from rl_agents_b200.agents.tree_search.deterministic import DeterministicPlannerAgent
+    from rl_agents_b200.envs import HighwayLiteEnv
+    from rl_agents_b200.evaluation import run_batched_episodes
+    seeds = [0, 1, 2, 3, 4]
+    out = run_batched_episodes("opd", seeds, 150, 0.8, max_steps=12, planner_seed=100)
+    for i, s in enumerate(seeds):
+        env = HighwayLiteEnv(seed=s)
+        agent = DeterministicPlannerAgent(env, {"budget": 150, "gamma": 0.8})
+        agent.seed(100 + i)
+        total, steps = 0.0, 0
+        for k in range(12):
+            a = agent.act(None)
+            assert a == out["actions"][i, k], (s, k)
+            _, r, term, trunc, _ = env.step(a)
+            total += np.float32(r)
+            steps += 1
+            if term or trunc:
+                break
+        assert steps == out["lengths"][i] and abs(total - out["returns"][i]) < 1e-6
+    mc = run_batched_episodes("mcts", seeds, 100, 0.8, max_steps=5)
+    ol = run_batched_episodes("olop", seeds, 100, 0.8, max_steps=5)
+    assert mc["lengths"].min() >= 1 and ol["lengths"].min() >= 1
