@@ -171,11 +171,11 @@ def test_batched_evaluation_equals_per_episode_agents():
             a = agent.act(None)
             assert a == out["actions"][i, k], (s, k)
             _, r, term, trunc, _ = env.step(a)
-            total += np.float32(r)
+            total += float(np.float32(r))
             steps += 1
             if term or trunc:
                 break
-        assert steps == out["lengths"][i] and abs(total - out["returns"][i]) < 1e-6
+        assert steps == out["lengths"][i] and abs(total - out["returns"][i]) < 1e-9
     mc = run_batched_episodes("mcts", seeds, 100, 0.8, max_steps=5)
     ol = run_batched_episodes("olop", seeds, 100, 0.8, max_steps=5)
     assert mc["lengths"].min() >= 1 and ol["lengths"].min() >= 1
