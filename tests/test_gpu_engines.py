@@ -85,6 +85,62 @@ def test_highway_step_batched_vs_oracle_random():
             assert int(flg[i].item()) == (1 if term else 0) | (2 if trunc else 0)
 
 
+def test_highway_step_exact_x_ties_take_the_scan_path():
+    """Two (or more) vehicles with exactly equal x cannot be ordered by the rank structure: the kernel
+    falls back to the literal scan of the spec (tie rules by slot index).  Also crashed and absent slots."""
+    import torch
+    from rl_agents_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    scenes = []
+    for seed in range(60, 72):
+        st = oenvs.make_highway_state(seed)
+        st.x[5] = st.x[3]                      # exact tie, usually on different lanes
+        st.x[9] = st.x[3]
+        if seed % 3 == 0:
+            st.y[5] = st.y[3]                  # same lane too: overlapping boxes -> crash at once
+        if seed % 4 == 0:
+            st.flags[11] = 0                   # an absent slot
+            st.flags[12] = 3                   # a vehicle that is already crashed
+        scenes.append(oenvs.HighwayLite(st))
+    n = len(scenes)
+    st = torch.tensor(np.stack([e.state.pack() for e in scenes]), dtype=torch.int32, device=dev)
+    rew = torch.empty(n, dtype=torch.float32, device=dev)
+    flg = torch.empty(n, dtype=torch.int32, device=dev)
+    for step in range(5):
+        acts = [int(e.get_available_actions()[step % len(e.get_available_actions())]) for e in scenes]
+        _lib.check(lib.b2_highway_step(_lib.ptr(st), _lib.ptr(torch.tensor(acts, dtype=torch.int32, device=dev)),
+                                       _lib.ptr(rew), _lib.ptr(flg), None, n, _lib.current_stream()))
+        got = st.cpu().numpy()
+        for i, e in enumerate(scenes):
+            _, r, term, trunc, _ = e.step(acts[i])
+            assert got[i].tolist() == e.state.pack().tolist(), (step, i)
+            assert float(rew[i].item()) == np.float32(r) and int(flg[i].item()) == (1 if term else 0) | (2 if trunc else 0)
+
+
+def test_highway_step_long_random_sweep_vs_oracle():
+    """200 scenes x 10 random decisions (30 000 physics sub-steps per implementation), bit for bit."""
+    import torch
+    from rl_agents_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    n = 200
+    scenes = [oenvs.HighwayLite(seed=1000 + i) for i in range(n)]
+    st = torch.tensor(np.stack([e.state.pack() for e in scenes]), dtype=torch.int32, device=dev)
+    rew = torch.empty(n, dtype=torch.float32, device=dev)
+    flg = torch.empty(n, dtype=torch.int32, device=dev)
+    rng = np.random.default_rng(5)
+    for step in range(10):
+        acts = [int(rng.choice(e.get_available_actions())) for e in scenes]
+        _lib.check(lib.b2_highway_step(_lib.ptr(st), _lib.ptr(torch.tensor(acts, dtype=torch.int32, device=dev)),
+                                       _lib.ptr(rew), _lib.ptr(flg), None, n, _lib.current_stream()))
+        got, r_got, f_got = st.cpu().numpy(), rew.cpu().numpy(), flg.cpu().numpy()
+        for i, e in enumerate(scenes):
+            _, r, term, trunc, _ = e.step(acts[i])
+            assert np.array_equal(got[i], e.state.pack()), (step, i)
+            assert r_got[i] == np.float32(r) and f_got[i] == (1 if term else 0) | (2 if trunc else 0)
+
+
 # ------------------------------------------------------------------- VI ----
 def vi_cases():
     rng = np.random.default_rng(0)
