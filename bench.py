@@ -207,17 +207,6 @@ def run_b200(a):
     def device_step(k):
         eng.plan(dev_scenes[k & 1])
 
-    plan_host = torch.empty(eng.plan_buf.shape, dtype=torch.int8).pin_memory()
-    res_host = torch.empty(eng.result.shape, dtype=torch.int32).pin_memory()
-    staging = torch.empty_like(dev_scenes[0])
-
-    def e2e_step(k):
-        staging.copy_(host_scenes[k & 1], non_blocking=True)            # H2D of this step's root scenes
-        eng.plan(staging)
-        plan_host.copy_(eng.plan_buf, non_blocking=True)                 # D2H of the step's results
-        res_host.copy_(eng.result, non_blocking=True)
-        stream.synchronize()                                             # the caller reads the plans
-
     for k in range(max(a.warmup, 3)):
         device_step(k)
     sampler = ClockSampler(local_rank)
@@ -229,10 +218,35 @@ def run_b200(a):
     res = eng.result.cpu().numpy()
     assert (res[:, 0] > n_exp).all() and (res[:, 4] == 0).all()
     mean_children = float((res[:, 0] - 1).mean() / n_exp)
+    # ---- e2e: the host-buffer C ABI (b2_opd_create / b2_opd_plan_host): pinned host scenes -> H2D -> search
+    #      -> D2H of plans and per-tree results, synchronous, every step ----
+    import ctypes
+    capacity, plan_capacity = eng.capacity, eng.plan_capacity
+    del eng
+    torch.cuda.empty_cache()
+    hc = _lib.OPDHostConfig(_lib.ENV_HIGHWAY, trees, N_ACTIONS, a.budget, int(a.keys_in_smem), a.kernel, a.gamma, 0.0,
+                            _lib.FiniteMDP())
+    handle = ctypes.c_void_p()
+    _lib.check(lib.b2_opd_create(ctypes.byref(hc), ctypes.byref(handle)))
+    plan_host = torch.empty((trees, plan_capacity), dtype=torch.int8).pin_memory()
+    res_host = torch.empty((trees, _lib.OPD_RESULT_WORDS), dtype=torch.int32).pin_memory()
+
+    def e2e_step(k):
+        _lib.check(lib.b2_opd_plan_host(handle, ctypes.c_void_p(host_scenes[k & 1].data_ptr()),
+                                        ctypes.c_void_p(plan_host.data_ptr()), ctypes.c_void_p(res_host.data_ptr())))
+
     for k in range(2):
         e2e_step(k)
-    ms_e2e = timed(e2e_step, a.steps)
-
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(a.steps):
+        e2e_step(k)
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t_e2e.item()) * 1e3
+    assert (res_host.numpy()[:, 0] > n_exp).all() and (res_host.numpy()[:, 4] == 0).all()
+    lib.b2_opd_destroy(handle)
     total_exp = float(world) * trees * n_exp * a.steps
     value = total_exp / (ms * 1e-3)
     e2e_value = total_exp / (ms_e2e * 1e-3)
@@ -266,11 +280,12 @@ def run_b200(a):
                    "budget": a.budget, "gamma": a.gamma, "trees_per_gpu": trees, "expansions_per_tree": n_exp,
                    "mean_children_per_expansion": mean_children, "child_nodes_per_s": value * mean_children,
                    "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)"
-                         % (trees * eng.capacity * (STATE_BYTES + NODE_BYTES) / 1e9),
+                         % (trees * capacity * (STATE_BYTES + NODE_BYTES) / 1e9),
                    "parallelism": "trees sharded over %d GPU(s), no data-path collective" % world,
                    "keys_in_smem": bool(a.keys_in_smem)},
         "e2e": {"value": e2e_value, "unit": "expansions/s", "h2d_bytes_per_step": int(trees * STATE_BYTES),
-                "d2h_bytes_per_step": int(plan_host.numel() + res_host.numel() * 4), "ms_per_step": ms_e2e / a.steps},
+                "d2h_bytes_per_step": int(plan_host.numel() + res_host.numel() * 4), "ms_per_step": ms_e2e / a.steps,
+                "path": "b2_opd_plan_host (C ABI, host buffers, synchronous); wall clock over the steps, max over ranks"},
         "gpu_launches": a.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

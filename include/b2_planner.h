@@ -162,6 +162,28 @@ int64_t b2_opd_workspace_bytes(const b2_opd_config* cfg);
 int b2_opd_plan(const b2_opd_config* cfg, const int32_t* root_states, const b2_opd_tree* tree,
                 void* workspace, int8_t* plan, int32_t* result, void* stream);
 
+/* Host-buffer convenience API (callers that do not manage CUDA memory: plain C, cgo, JNI ...).
+ * A handle owns the device arena of a batch of trees; *_host pointers are ordinary host memory
+ * (pinned memory makes the copies asynchronous); b2_opd_plan_host is synchronous. */
+typedef struct b2_opd_handle b2_opd_handle;
+typedef struct b2_opd_host_config {
+    int32_t env_kind, n_trees, n_actions;
+    int32_t budget;          /* config["budget"]; n_expansions = budget / n_actions (:118) */
+    int32_t keys_in_smem, kernel;
+    double gamma;            /* config["gamma"], 0 <= gamma < 1                     */
+    double terminal_reward;
+    b2_finite_mdp mdp;       /* HOST tables when env_kind == B2_ENV_FINITE          */
+} b2_opd_host_config;
+int b2_opd_create(const b2_opd_host_config* cfg, b2_opd_handle** out);
+void b2_opd_destroy(b2_opd_handle* h);
+int32_t b2_opd_plan_capacity(const b2_opd_handle* h);   /* bytes per tree in plan_host */
+/* root_states_host: [n_trees] state ids or [n_trees,136] words; plan_host: int8
+ * [n_trees, plan_capacity]; result_host: int32 [n_trees, B2_OPD_RESULT_WORDS]. */
+int b2_opd_plan_host(b2_opd_handle* h, const int32_t* root_states_host, int8_t* plan_host, int32_t* result_host);
+/* Node arrays of one tree (first n_nodes entries) to host buffers; any pointer may be NULL. */
+int b2_opd_copy_tree(b2_opd_handle* h, int32_t tree, int32_t n_nodes, int32_t* parent, int32_t* first_child,
+                     int32_t* count, int32_t* meta, double* reward, double* lower, double* upper);
+
 /* ------------------------------------------------------------------------
  * MCTS -- rl_agents/agents/tree_search/mcts.py (open loop)
  * ---------------------------------------------------------------------- */

@@ -46,6 +46,12 @@ class OPDTree(ctypes.Structure):
                                         "lower", "upper", "state")]
 
 
+class OPDHostConfig(ctypes.Structure):
+    _fields_ = [("env_kind", c_int32), ("n_trees", c_int32), ("n_actions", c_int32), ("budget", c_int32),
+                ("keys_in_smem", c_int32), ("kernel", c_int32), ("gamma", c_double), ("terminal_reward", c_double),
+                ("mdp", FiniteMDP)]
+
+
 class MCTSConfig(ctypes.Structure):
     _fields_ = [("env_kind", c_int32), ("n_trees", c_int32), ("n_actions", c_int32), ("episodes", c_int32),
                 ("horizon", c_int32), ("node_capacity", c_int32), ("rollout_policy", c_int32),
@@ -78,6 +84,11 @@ EXPORTS = {
     "b2_opd_workspace_bytes": (c_int64, [ctypes.POINTER(OPDConfig)]),
     "b2_opd_plan": (c_int, [ctypes.POINTER(OPDConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
                             c_void_p, c_void_p]),
+    "b2_opd_create": (c_int, [ctypes.POINTER(OPDHostConfig), ctypes.POINTER(c_void_p)]),
+    "b2_opd_destroy": (None, [c_void_p]),
+    "b2_opd_plan_capacity": (c_int32, [c_void_p]),
+    "b2_opd_plan_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2_opd_copy_tree": (c_int, [c_void_p, c_int32, c_int32] + [c_void_p] * 7),
     "b2_mcts_plan": (c_int, [ctypes.POINTER(MCTSConfig), c_void_p, ctypes.POINTER(MCTSTree), c_void_p, c_void_p,
                              c_void_p, c_void_p]),
     "b2_olop_plan": (c_int, [ctypes.POINTER(OLOPConfig), c_void_p, ctypes.POINTER(OLOPTree), c_void_p, c_void_p,
