@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--trees", type=int, default=0, help="decisions per GPU per step (default 64 per SM)")
+    ap.add_argument("--trees", type=int, default=0, help="decisions per GPU per step (default 128 per SM, capped by free HBM)")
     ap.add_argument("--budget", type=int, default=BUDGET)
     ap.add_argument("--gamma", type=float, default=GAMMA)
     ap.add_argument("--keys-in-smem", type=int, default=0)
@@ -174,8 +174,16 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    trees = a.trees or 64 * sms
     n_exp = a.budget // N_ACTIONS
+    if a.trees:
+        trees = a.trees
+    else:
+        # default batch: 128 decisions per SM (more work in flight = better overlap of the trees' phases),
+        # capped so that the tree arena (scene + node record + frontier key per node) takes <= 65 % of the free HBM
+        per_tree = (1 + n_exp * N_ACTIONS) * (STATE_BYTES + NODE_BYTES + 8) + 16 * 1024
+        free, _ = torch.cuda.mem_get_info(dev)
+        trees = min(128 * sms, int(0.65 * free / per_tree))
+        trees = max(8 * sms, trees // (8 * sms) * (8 * sms))
 
     eng = OPDEngine(_lib.ENV_HIGHWAY, trees, N_ACTIONS, a.budget, a.gamma, keys_in_smem=bool(a.keys_in_smem),
                     device=dev, kernel=a.kernel)
