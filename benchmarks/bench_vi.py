@@ -90,11 +90,12 @@ def main():
                         "unit": "GB/s", "frac": slab_bytes / (per_sweep_ms * 1e-3) / 1e9 / peak,
                         "bytes_per_sweep_per_gpu": slab_bytes}}
     if rank == 0 and world == 1 and a.cpu_sweeps > 0 and a.mode == "sparse":
-        from oracle import planners
         v = np.zeros(S)
         t0 = time.perf_counter()
-        for _ in range(a.cpu_sweeps):
-            q = planners.bellman_expectation("sparse", P, R, term, v, 0.95, nxt=N)
+        for _ in range(a.cpu_sweeps):      # the reference's sparse Bellman operator in numpy (value_iteration.py:56-63)
+            next_v = (P * np.take(v, N)).sum(axis=-1)
+            next_v[term] = 0
+            q = R + 0.95 * next_v
             v = q.max(axis=-1)
         dt = (time.perf_counter() - t0) / a.cpu_sweeps
         out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "sweeps/s", "cores": 1, "kind": "port",
