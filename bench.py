@@ -117,6 +117,28 @@ def cpu_baseline(budget, gamma):
                       % (budget, n_exp, dt)}
 
 
+def cpu_port_c(budget, gamma):
+    """The C restatement (oracle/c: same spec, literal O(V^2) scans, heap frontier) on one core and on all
+    host threads -- what an optimised CPU implementation of the same path does, next to the Python port."""
+    from concurrent.futures import ThreadPoolExecutor
+    import numpy as np
+    from oracle import c_oracle
+    from oracle import envs as oenvs
+    scenes = [oenvs.make_highway_state(s).pack() for s in range(2 * (os.cpu_count() or 1))]
+    c_oracle.opd_plan(scenes[0], 500, gamma)
+    t0 = time.perf_counter()
+    c_oracle.opd_plan(scenes[0], budget, gamma)
+    single = (budget // N_ACTIONS) / (time.perf_counter() - t0)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(lambda w: c_oracle.opd_plan(w, budget, gamma), scenes))
+    multi = len(scenes) * (budget // N_ACTIONS) / (time.perf_counter() - t0)
+    return {"value": multi, "unit": "expansions/s", "cores": cores, "single_core_value": single, "kind": "port",
+            "sample": "oracle/c OPD, HighwayLite, budget %d (full C2 budget): 1 plan() on one core; %d plan()s on %d threads"
+                      % (budget, len(scenes), cores)}
+
+
 def run_reference(a):
     """--impl reference: oracle port on all host cores, one plan() per process."""
     rank = int(os.environ.get("RANK", "0"))
@@ -304,6 +326,10 @@ def run_b200(a):
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(a.cpu_budget, a.gamma)
+        try:
+            out["cpu_port_c"] = cpu_port_c(a.budget, a.gamma)
+        except Exception as e:      # the C oracle is optional test infrastructure
+            out["cpu_port_c"] = {"unavailable": str(e)[:200]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -1,0 +1,63 @@
+"""ctypes wrapper of the C oracle (oracle/c) -- TEST INFRASTRUCTURE.  Third statement of the
+HighwayLite spec and a literal C OPD; pinned bit-exactly against oracle/envs.py and
+oracle/planners.py (tests/test_c_oracle.py), hence against the reference's golden vectors."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c")
+LIB = os.path.join(HERE, "liboracle_c.so")
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, f) for f in ("highway_lite.c", "opd.c", "highway_lite.h", "Makefile")]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.run(["make", "-C", HERE, "-s", "-B"], check=True)
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(LIB)
+        _lib.opd_highway_plan.restype = ctypes.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def step_batch(words, actions):
+    """words [n,136] int32 (updated copy returned), actions [n] -> (words, rewards f32, flags)."""
+    lib = load()
+    w = np.ascontiguousarray(words, dtype=np.int32).copy()
+    a = np.ascontiguousarray(actions, dtype=np.int32)
+    r = np.zeros(len(a), dtype=np.float32)
+    f = np.zeros(len(a), dtype=np.int32)
+    lib.hl_step_batch(_p(w), _p(a), _p(r), _p(f), ctypes.c_int(len(a)))
+    return w, r, f
+
+
+def opd_plan(root_words, budget, gamma, terminal_reward=0.0):
+    """Returns a dict of node arrays in creation order (same fields as oracle.planners.Tree)."""
+    lib = load()
+    cap = 1 + (int(budget) // 5) * 5
+    i32 = {k: np.zeros(cap, dtype=np.int32) for k in ("parent", "action", "depth", "count", "first_child",
+                                                      "n_children", "done")}
+    f64 = {k: np.zeros(cap, dtype=np.float64) for k in ("reward", "lower", "upper")}
+    n_leaves = ctypes.c_int32(0)
+    root = np.ascontiguousarray(root_words, dtype=np.int32)
+    n = lib.opd_highway_plan(_p(root), ctypes.c_int(int(budget)), ctypes.c_double(gamma), ctypes.c_double(terminal_reward),
+                             _p(i32["parent"]), _p(i32["action"]), _p(i32["depth"]), _p(i32["count"]),
+                             _p(i32["first_child"]), _p(i32["n_children"]), _p(i32["done"]), _p(f64["reward"]),
+                             _p(f64["lower"]), _p(f64["upper"]), ctypes.byref(n_leaves))
+    if n < 0:
+        raise ValueError("This planner assumes that all rewards are normalized in [0, 1]")
+    out = {k: v[:n] for k, v in {**i32, **f64}.items()}
+    out["n_leaves"] = n_leaves.value
+    return out
