@@ -598,3 +598,21 @@ def test_edge_cases_small_budgets_and_argument_validation():
     m.cfg.rollout_policy = 7
     with pytest.raises(_lib.B2Error, match="policy"):
         m.plan(torch.zeros(1, dtype=torch.int32, device="cuda"), pcg64_words(np_random(0)).reshape(1, -1))
+
+
+def test_opd_highway_c2_full_size_batch_vs_c_oracle():
+    """C2 at full size, many decisions: 24 scenes x budget 10 000 through the batch kernel, every node
+    array of every tree bit-identical with the C oracle (itself pinned to the reference's golden tree)."""
+    from oracle import c_oracle
+    seeds = list(range(500, 524))
+    words = [oenvs.make_highway_state(s).pack() for s in seeds]
+    eng, plans, res = run_opd_highway(words, 10000, 0.8)
+    for i, w in enumerate(words):
+        t = c_oracle.opd_plan(w, 10000, 0.8)
+        d = eng.tree_dict(i)
+        assert res[i, 0] == len(t["parent"]) and res[i, 1] == t["n_leaves"]
+        for k in ("parent", "action", "count", "depth", "first_child", "n_children"):
+            assert np.array_equal(np.asarray(d[k], dtype=np.int64), t[k].astype(np.int64)), (i, k)
+        assert np.array_equal(d["done"], t["done"].astype(bool))
+        for k in ("reward", "lower", "upper"):
+            assert np.array_equal(d[k], t[k]), (i, k)
