@@ -13,7 +13,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("highway_lite.c", "opd.c", "highway_lite.h", "Makefile")]
+    srcs = [os.path.join(HERE, f) for f in ("highway_lite.c", "opd.c", "mcts.c", "highway_lite.h", "Makefile")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.run(["make", "-C", HERE, "-s", "-B"], check=True)
     return LIB
@@ -25,6 +25,7 @@ def load():
         build()
         _lib = ctypes.CDLL(LIB)
         _lib.opd_highway_plan.restype = ctypes.c_int
+        _lib.mcts_highway_plan.restype = ctypes.c_int
     return _lib
 
 
@@ -61,3 +62,23 @@ def opd_plan(root_words, budget, gamma, terminal_reward=0.0):
     out = {k: v[:n] for k, v in {**i32, **f64}.items()}
     out["n_leaves"] = n_leaves.value
     return out
+
+
+def mcts_plan(root_words, episodes, horizon, gamma, temperature, rng_words):
+    """rng_words: uint64[6] numpy PCG64 state (advanced copy returned).  Returns (tree dict, rng_words)."""
+    lib = load()
+    cap = 1 + int(episodes) * 5
+    i32 = {k: np.zeros(cap, dtype=np.int32) for k in ("parent", "action", "count", "first_child", "n_children")}
+    f64 = {k: np.zeros(cap, dtype=np.float64) for k in ("value", "prior")}
+    cdf = np.ones((6, 5), dtype=np.float64)
+    for n in range(1, 6):
+        c = (np.ones(n) / n).cumsum()
+        c /= c[-1]
+        cdf[n, :n] = c
+    words = np.ascontiguousarray(rng_words, dtype=np.uint64).copy()
+    root = np.ascontiguousarray(root_words, dtype=np.int32)
+    n = lib.mcts_highway_plan(_p(root), ctypes.c_int(int(episodes)), ctypes.c_int(int(horizon)), ctypes.c_double(gamma),
+                              ctypes.c_double(temperature), _p(words), _p(cdf), _p(i32["parent"]), _p(i32["action"]),
+                              _p(i32["count"]), _p(i32["first_child"]), _p(i32["n_children"]), _p(f64["value"]),
+                              _p(f64["prior"]))
+    return {k: v[:n] for k, v in {**i32, **f64}.items()}, words

@@ -54,3 +54,21 @@ def test_c_opd_matches_reference_golden_trees():
     tc = c_oracle.opd_plan(oenvs.make_highway_state(9).pack(), 200, 0.85)
     assert tc["parent"].tolist() == tp.parent and tc["count"].tolist() == tp.count
     assert np.array_equal(tc["upper"], np.array(tp.upper)) and np.array_equal(tc["lower"], np.array(tp.lower))
+
+
+def test_c_mcts_matches_reference_golden_and_python_restatement():
+    from oracle.pcg64 import PCG64
+
+    def words(seed):
+        return PCG64.from_numpy(np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))).words()
+    for key in sorted(H["mcts"]):
+        g = H["mcts"][key]
+        t, _ = c_oracle.mcts_plan(np.array(H["states"][key[1]], dtype=np.int32), g["episodes"], g["horizon"],
+                                  g["config"]["gamma"], g["temperature"], words(g["seed"]))
+        assert_tree_matches(t, g["tree"], ["value", "prior"])
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(11)))
+    plan, tp = planners.mcts_plan(oenvs.HighwayLite(seed=8), 150, 7, 0.85, 10.0, rng)
+    tc, w = c_oracle.mcts_plan(oenvs.make_highway_state(8).pack(), 150, 7, 0.85, 10.0, words(11))
+    assert tc["parent"].tolist() == tp.parent and tc["count"].tolist() == tp.count and tc["action"].tolist() == tp.action
+    assert np.array_equal(tc["value"], np.array(tp.value))
+    assert w.tolist() == PCG64.from_numpy(rng).words().tolist()          # same stream position afterwards

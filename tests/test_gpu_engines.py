@@ -616,3 +616,22 @@ def test_opd_highway_c2_full_size_batch_vs_c_oracle():
         assert np.array_equal(d["done"], t["done"].astype(bool))
         for k in ("reward", "lower", "upper"):
             assert np.array_equal(d[k], t[k]), (i, k)
+
+
+def test_mcts_highway_c3_full_size_vs_c_oracle():
+    """C3 at full size (4096 episodes x horizon 20): every node statistic and the RNG stream position
+    bit-identical with the C oracle (itself pinned to the reference's golden MCTS trees)."""
+    from oracle import c_oracle
+    from oracle.pcg64 import PCG64
+    from rl_agents_b200 import _lib
+    seeds = [70, 71, 72]
+    words = [oenvs.make_highway_state(s).pack() for s in seeds]
+    eng, plans, res, rng_words, gens = run_mcts(_lib.ENV_HIGHWAY, words, 4096, 20, 0.8, 10.0, [1, 2, 3])
+    for i in range(len(seeds)):
+        t, w = c_oracle.mcts_plan(words[i], 4096, 20, 0.8, 10.0, PCG64.from_numpy(np_random(i + 1)).words())
+        d = eng.tree_dict(i)
+        assert res[i, 0] == len(t["parent"])
+        for k in ("parent", "action", "count", "first_child", "n_children"):
+            assert np.array_equal(np.asarray(d[k], dtype=np.int64), t[k].astype(np.int64)), (i, k)
+        assert np.array_equal(d["value"], t["value"]) and np.array_equal(d["prior"], t["prior"])
+        assert rng_words[i].tolist() == w.tolist()
