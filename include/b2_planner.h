@@ -201,6 +201,10 @@ typedef struct b2_mcts_config {
     const double* uniform_cdf; /* [(n_actions+1), n_actions]: row n = cumsum(ones(n)/n)/last,
                                   the cdf Generator.choice(a, 1, p) searches (host numpy)  */
     b2_finite_mdp mdp;
+    const int32_t* resume_nodes; /* nullable [n_trees]: > 0 -> the tree arrays already hold that many nodes
+                                    (a re-rooted sub-tree, step_strategy "subtree", abstract.py:195-206,
+                                    mcts.py:129-130) and the search continues from them; the caller sizes
+                                    node_capacity >= resume + episodes * n_actions                      */
 } b2_mcts_config;
 
 typedef struct b2_mcts_tree {

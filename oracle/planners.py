@@ -171,13 +171,41 @@ def _policy(policy_config, state):
     raise ValueError("Unknown policy type")
 
 
+def mcts_reroot(t, action):
+    """AbstractPlanner.step_by_subtree (abstract.py:195-206): the sub-tree under the root's child `action`
+    becomes the tree (re-indexed breadth first); None when that action was never expanded."""
+    child = next((c for c in t.children(0) if t.action[c] == action), None)
+    if child is None:
+        return None
+    order, new_parent = [child], [-1]
+    head = 0
+    while head < len(order):
+        for c in t.children(order[head]):
+            order.append(c)
+            new_parent.append(head)
+        head += 1
+    pos = {old: new for new, old in enumerate(order)}
+    s = Tree()
+    s.parent = new_parent
+    s.action = [-1] + [t.action[o] for o in order[1:]]
+    s.depth = [t.depth[o] - t.depth[child] for o in order]
+    s.count = [t.count[o] for o in order]
+    s.n_children = [t.n_children[o] for o in order]
+    s.first_child = [pos[t.first_child[o]] if t.n_children[o] > 0 else -1 for o in order]
+    s.value = [t.value[o] for o in order]
+    s.prior = [t.prior[o] for o in order]
+    return s
+
+
 def mcts_plan(env, episodes, horizon, gamma, temperature, np_random,
-              prior_policy=None, rollout_policy=None):
-    """MCTS.plan (mcts.py:179-184) from a fresh root.  Returns (plan, tree)."""
+              prior_policy=None, rollout_policy=None, tree=None):
+    """MCTS.plan (mcts.py:179-184) from a fresh root, or continuing `tree` (step_strategy "subtree").
+    Returns (plan, tree)."""
     prior_policy = prior_policy or {"type": "random_available"}
     rollout_policy = rollout_policy or {"type": "random_available"}
-    t = Tree()
-    t.value, t.prior = [], []
+    t = tree if tree is not None else Tree()
+    if tree is None:
+        t.value, t.prior = [], []
 
     def new_node(parent, action, depth, prior):
         t.parent.append(parent)
@@ -190,7 +218,8 @@ def mcts_plan(env, episodes, horizon, gamma, temperature, np_random,
         t.prior.append(prior)
         return len(t.parent) - 1
 
-    new_node(-1, -1, 0, 1)
+    if tree is None:
+        new_node(-1, -1, 0, 1)
     for _ in range(episodes):
         state = copy.deepcopy(env)                              # :183
         node, total, depth, terminal = 0, 0, 0, False

@@ -46,11 +46,35 @@ class MCTS(AbstractPlanner):
         key = (d.kind, d.n_actions, replicas, episodes, self.config["horizon"], self.config["gamma"],
                self.config["temperature"], id(d.mdp))
         if key != self._engine_key:
+            # "subtree" keeps nodes alive for up to `horizon` decisions (a node at depth d survives d re-rootings)
+            capacity = None
+            if self.config["step_strategy"] == "subtree":
+                capacity = 1 + (self.config["horizon"] + 1) * episodes * d.n_actions
             self.engine = MCTSEngine(d.kind, replicas, d.n_actions, episodes, self.config["horizon"],
                                      self.config["gamma"], self.config["temperature"], mdp=d.mdp,
-                                     rollout_policy=self.rollout_policy, prior_policy=self.prior_policy)
+                                     rollout_policy=self.rollout_policy, prior_policy=self.prior_policy,
+                                     capacity=capacity)
             self._engine_key = key
+            self._resume = 0
         return self.engine
+
+    def reset(self):
+        super(MCTS, self).reset()
+        self._resume = 0
+
+    def step_tree(self, actions):
+        """abstract.py:172-187: "reset" (default) or "subtree" (works for MCTS in the reference); "prior" is
+        unreachable in the reference (mcts.py:186-190 is never called) and resets with a warning there too."""
+        if self.config["step_strategy"] == "subtree":
+            if actions and self.engine is not None and int(self.config.get("root_parallel", 1) or 1) <= 1 \
+                    and self.last_tree is self.engine:
+                self._resume = self.engine.reroot(0, actions[0])          # step_by_subtree (:195-206)
+                if self._resume == 0:
+                    self.step_by_reset()
+            else:
+                self.step_by_reset()
+        else:
+            super(MCTS, self).step_tree(actions)
 
     def plan(self, state, observation):
         import torch
@@ -61,7 +85,9 @@ class MCTS(AbstractPlanner):
         if replicas <= 1:
             # the reference's semantics: one tree, strict episode order, the planner's own RNG stream
             eng = self._engine_for(d, 1, self.config["episodes"])
-            eng.plan(root.to(eng.device).contiguous(), pcg64_words(self.np_random).reshape(1, -1))
+            resume = [self._resume] if getattr(self, "_resume", 0) > 0 else None
+            eng.plan(root.to(eng.device).contiguous(), pcg64_words(self.np_random).reshape(1, -1), resume)
+            self._resume = 0
             plans, res, rng_words = eng.finish()
             set_pcg64_words(self.np_random, rng_words[0])     # the device consumed the planner's stream
             self.last_tree = eng

@@ -81,12 +81,13 @@ __global__ void __launch_bounds__(128, B2_MCTS_MIN_BLOCKS) mcts_kernel(MctsArgs 
 
     Pcg64 rng;
     rng.load(a.rng + (int64_t)tree * B2_PCG64_STATE_WORDS);
-    if (writer) {   // MCTSNode(parent=None) (mcts.py:129-130, :207-210)
+    const int resume = a.cfg.resume_nodes ? a.cfg.resume_nodes[tree] : 0;
+    if (writer && resume <= 0) {   // MCTSNode(parent=None) (mcts.py:129-130, :207-210)
         tr.parent[nb] = -1; tr.first_child[nb] = -1; tr.count[nb] = 0; tr.meta[nb] = 0xff;
         tr.value[nb] = 0.0; tr.prior[nb] = 1.0;
     }
     __syncwarp(gmask);
-    int n_nodes = 1, env_steps = 0;
+    int n_nodes = resume > 0 ? resume : 1, env_steps = 0;   // resume: a re-rooted sub-tree is already in place
 
     for (int ep = 0; ep < a.cfg.episodes; ++ep) {
         Env env;

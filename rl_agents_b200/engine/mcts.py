@@ -26,12 +26,44 @@ def set_pcg64_words(gen, w):
     gen.bit_generator.state = st
 
 
+def reroot_arrays(arrays, n, action):
+    """step_by_subtree (abstract.py:195-206): keep the sub-tree under the root's child `action`, re-indexed
+    breadth first (children of a node stay contiguous and in order) with that child as node 0.
+    arrays: dict of numpy arrays parent / first_child / count / meta / value / prior (first n entries valid).
+    Returns (new arrays dict, number of kept nodes) -- (None, 0) when the action was never expanded."""
+    fc, meta = arrays["first_child"], arrays["meta"]
+    root_child = -1
+    if fc[0] >= 0:
+        for c in range(fc[0], fc[0] + ((meta[0] >> 8) & 0xff)):
+            if (meta[c] & 0xff) == action:
+                root_child = c
+    if root_child < 0:
+        return None, 0
+    order, new_parent = [root_child], [-1]
+    head = 0
+    new_first = []
+    while head < len(order):
+        old = order[head]
+        k = (meta[old] >> 8) & 0xff if fc[old] >= 0 else 0
+        new_first.append(len(order) if k else -1)
+        for c in range(fc[old], fc[old] + k):
+            order.append(c)
+            new_parent.append(head)
+        head += 1
+    order = np.array(order)
+    out = {"parent": np.array(new_parent, dtype=np.int32), "first_child": np.array(new_first, dtype=np.int32),
+           "count": arrays["count"][order].copy(), "meta": arrays["meta"][order].copy(),
+           "value": arrays["value"][order].copy(), "prior": arrays["prior"][order].copy()}
+    out["meta"][0] = (out["meta"][0] & ~0xff) | 0xff          # the new root has no incoming action
+    return out, len(order)
+
+
 class MCTSEngine(object):
     """n_trees independent MCTS decisions per launch; every tree consumes its
     own numpy PCG64 stream exactly as the reference planner would."""
 
     def __init__(self, env_kind, n_trees, n_actions, episodes, horizon, gamma, temperature, mdp=None,
-                 rollout_policy="random_available", prior_policy="random_available", device="cuda"):
+                 rollout_policy="random_available", prior_policy="random_available", device="cuda", capacity=None):
         import torch
         self.torch = torch
         self.lib = _lib.load()
@@ -41,7 +73,7 @@ class MCTSEngine(object):
                 raise ValueError("Unknown policy type")
         self.n_trees, self.n_actions = int(n_trees), int(n_actions)
         self.episodes, self.horizon = int(episodes), int(horizon)
-        self.capacity = 1 + self.episodes * self.n_actions
+        self.capacity = max(int(capacity or 0), 1 + self.episodes * self.n_actions)
         gp, _ = gamma_tables(gamma, self.horizon + 1)
         self.gamma_pow = torch.as_tensor(gp, device=self.device)
         self.cdf = torch.as_tensor(uniform_cdf_table(self.n_actions), device=self.device)
@@ -57,16 +89,23 @@ class MCTSEngine(object):
         self.cfg = _lib.MCTSConfig(env_kind, self.n_trees, self.n_actions, self.episodes, self.horizon, self.capacity,
                                    POLICIES[rollout_policy], POLICIES[prior_policy], float(temperature),
                                    self.gamma_pow.data_ptr(), self.cdf.data_ptr(),
-                                   self.tables.struct() if self.tables else _lib.FiniteMDP())
+                                   self.tables.struct() if self.tables else _lib.FiniteMDP(), None)
+        self.resume = torch.zeros(self.n_trees, dtype=i32, device=self.device)
         self.tree = _lib.MCTSTree(*[t.data_ptr() for t in (self.parent, self.first_child, self.count, self.meta,
                                                            self.value, self.prior)])
         self.plan_buf = torch.empty((self.n_trees, max(self.horizon, 1)), dtype=torch.int8, device=self.device)
         self.result = torch.empty((self.n_trees, _lib.MCTS_RESULT_WORDS), dtype=i32, device=self.device)
         self.rng = torch.empty((self.n_trees, _lib.PCG64_STATE_WORDS), dtype=torch.int64, device=self.device)
 
-    def plan(self, root_states, rng_words):
-        """rng_words: uint64 [n_trees, 6] numpy (pcg64_words per tree)."""
+    def plan(self, root_states, rng_words, resume_nodes=None):
+        """rng_words: uint64 [n_trees, 6] numpy (pcg64_words per tree).  resume_nodes: per-tree node counts of
+        re-rooted sub-trees already in the arrays (see reroot), or None for fresh trees."""
         self.rng.copy_(self.torch.from_numpy(np.ascontiguousarray(rng_words).view(np.int64)))
+        if resume_nodes is None:
+            self.cfg.resume_nodes = None
+        else:
+            self.resume.copy_(self.torch.as_tensor(np.asarray(resume_nodes, dtype=np.int32)))
+            self.cfg.resume_nodes = self.resume.data_ptr()
         _lib.check(self.lib.b2_mcts_plan(self.cfg, _lib.ptr(root_states), self.tree, _lib.ptr(self.rng),
                                          _lib.ptr(self.plan_buf), _lib.ptr(self.result), _lib.current_stream()))
 
@@ -76,6 +115,19 @@ class MCTSEngine(object):
         plans_dev = self.plan_buf.cpu().numpy()
         plans = [plans_dev[i, :res[i, 1]].astype(int).tolist() for i in range(self.n_trees)]
         return plans, res, self.rng.cpu().numpy().view(np.uint64)
+
+    def reroot(self, tree, action):
+        """Keep the sub-tree under root child `action` of `tree` (host-side compaction, once per decision).
+        Returns the number of nodes kept (0: the action was never expanded -> start a new tree)."""
+        n = int(self.result[tree, 0].item())
+        names = ("parent", "first_child", "count", "meta", "value", "prior")
+        arrays = {k: getattr(self, k)[tree, :n].cpu().numpy() for k in names}
+        out, kept = reroot_arrays(arrays, n, int(action))
+        if kept + self.episodes * self.n_actions > self.capacity:
+            return 0                                   # would not fit: fall back to a fresh tree
+        for k in names if kept else ():
+            getattr(self, k)[tree, :kept] = self.torch.as_tensor(out[k], device=self.device)
+        return kept
 
     def tree_dict(self, tree=0):
         n = int(self.result[tree, 0].item())

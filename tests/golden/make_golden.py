@@ -217,6 +217,30 @@ def main():
     mc["large1_terminal_b600_g0.9"] = run_mcts(finite(T, R, termx), {"budget": 600, "gamma": 0.9}, seed=1)
     out["mcts"] = mc
 
+    # ---------------- MCTS with step_strategy "subtree": two consecutive decisions ----------------
+    def canonical(root):
+        nodes, head = [root], 0
+        rows = []
+        while head < len(nodes):
+            nd = nodes[head]
+            rows.append([len(nd.children), int(nd.count), float(nd.value), float(nd.prior)])
+            nodes.extend(nd.children.values())
+            head += 1
+        return rows
+    env_s = finite()
+    agent = ref_mcts.MCTSAgent(env_s, {"budget": 300, "gamma": 0.85, "step_strategy": "subtree"})
+    agent.seed(4)
+    sub = {"plans": [], "trees": [], "states": []}
+    for _ in range(3):
+        sub["states"].append(int(env_s.mdp.state))
+        plan = agent.plan(None)
+        sub["plans"].append([int(a) for a in plan])
+        sub["trees"].append(canonical(agent.planner.root))
+        env_s.step(plan[0])
+    sub["episodes"], sub["horizon"] = int(agent.planner.config["episodes"]), int(agent.planner.config["horizon"])
+    sub["temperature"] = float(agent.planner.config["temperature"])
+    out["mcts_subtree"] = sub
+
     # ---------------- OLOP (KL) on finite ----------------
     ol = {}
     kl_cfg = {"budget": 200, "gamma": 0.9, "continuation_type": "uniform",

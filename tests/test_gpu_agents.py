@@ -179,3 +179,23 @@ def test_batched_evaluation_equals_per_episode_agents():
     mc = run_batched_episodes("mcts", seeds, 100, 0.8, max_steps=5)
     ol = run_batched_episodes("olop", seeds, 100, 0.8, max_steps=5)
     assert mc["lengths"].min() >= 1 and ol["lengths"].min() >= 1
+
+
+def test_mcts_agent_subtree_strategy_matches_reference():
+    """step_strategy "subtree": the tree is re-rooted at the executed action between decisions
+    (host compaction) and the kernel resumes from it; three decisions against the reference."""
+    from rl_agents_b200.agents.tree_search.mcts import MCTSAgent
+    from tests.util import canonical_tree
+    g = G["mcts_subtree"]
+    env = finite_env()
+    agent = MCTSAgent(env, {"budget": 300, "gamma": 0.85, "step_strategy": "subtree"})
+    agent.seed(4)
+    for k in range(3):
+        assert env.mdp.state == g["states"][k]
+        plan = agent.plan(None)
+        assert plan == g["plans"][k], k
+        d = agent.planner.last_tree.tree_dict(0)
+        got = canonical_tree(d["first_child"], d["n_children"], [d["count"].tolist(), d["value"].tolist(),
+                                                                 d["prior"].tolist()])
+        assert got == g["trees"][k], k
+        env.step(plan[0])

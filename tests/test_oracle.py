@@ -64,6 +64,47 @@ def test_mcts_finite(key):
     assert_tree_matches(tree_dict(t, ["value", "prior"]), g["tree"], ["value", "prior"])
 
 
+def test_mcts_subtree_reuse_matches_reference():
+    """step_strategy "subtree" (abstract.py:172-206): three consecutive decisions, the tree re-rooted at the
+    executed action in between; compared in an id-independent breadth-first form."""
+    from tests.util import canonical_tree
+    g = G["mcts_subtree"]
+    env = finite()
+    rng = np_random(4)
+    tree = None
+    for k in range(3):
+        assert env.mdp.state == g["states"][k]
+        plan, tree = planners.mcts_plan(env, g["episodes"], g["horizon"], 0.85, g["temperature"], rng, tree=tree)
+        assert plan == g["plans"][k]
+        got = canonical_tree(tree.first_child, tree.n_children, [tree.count, tree.value, tree.prior])
+        assert got == g["trees"][k], k
+        env.step(plan[0])
+        tree = planners.mcts_reroot(tree, plan[0])
+
+
+def test_reroot_arrays_equals_oracle_reroot():
+    from rl_agents_b200.engine.mcts import reroot_arrays
+    from tests.util import canonical_tree
+    _, t = planners.mcts_plan(finite(), 44, 9, 0.8, 10.0, np_random(1))
+    meta = np.array([(a & 0xff) | (n << 8) for a, n in zip(t.action, t.n_children)], dtype=np.int32)
+    arrays = {"parent": np.array(t.parent, dtype=np.int32), "first_child": np.array(t.first_child, dtype=np.int32),
+              "count": np.array(t.count, dtype=np.int32), "meta": meta, "value": np.array(t.value),
+              "prior": np.array(t.prior)}
+    for action in range(5):
+        ref = planners.mcts_reroot(t, action)
+        out, kept = reroot_arrays(arrays, len(t), action)
+        if ref is None:
+            assert kept == 0
+            continue
+        assert kept == len(ref)
+        assert out["parent"].tolist() == ref.parent and out["first_child"].tolist() == ref.first_child
+        assert out["count"].tolist() == ref.count and np.array_equal(out["value"], np.array(ref.value))
+        assert ((out["meta"] >> 8) & 0xff).tolist() == ref.n_children
+        assert (out["meta"][1:] & 0xff).tolist() == ref.action[1:] and (out["meta"][0] & 0xff) == 0xff
+        assert canonical_tree(ref.first_child, ref.n_children, [ref.count]) == \
+            canonical_tree(out["first_child"], (out["meta"] >> 8) & 0xff, [out["count"].tolist()])
+
+
 @pytest.mark.parametrize("key", sorted(G["olop"]))
 def test_olop_finite(key):
     g = G["olop"][key]

@@ -57,3 +57,14 @@ def assert_tree_matches(got, golden, float_fields, exact=True, rtol=0.0, atol=0.
                     np.testing.assert_allclose(val, golden[key], rtol=max(rtol, 1e-12), err_msg=key)
             elif key != "n_nodes":
                 assert val == golden[key], key
+
+
+def canonical_tree(first_child, n_children, fields):
+    """Breadth-first listing (children in stored order) of per-node tuples: an id-independent form
+    for comparing trees whose node numbering differs (re-rooted sub-trees)."""
+    order, head = [0], 0
+    while head < len(order):
+        n = order[head]
+        order.extend(range(first_child[n], first_child[n] + n_children[n]) if n_children[n] > 0 else [])
+        head += 1
+    return [[int(n_children[i])] + [f[i] for f in fields] for i in order]
