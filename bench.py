@@ -300,6 +300,18 @@ def run_b200(a):
     except Exception:
         pass
 
+    ncu = None      # static evidence from the committed ncu capture of this kernel (not measured in this run)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_opd_highway_multi_ncu_summary.json")) as f:
+            summ = json.load(f)
+        ncu = {"source": "profiles/r01_opd_highway_multi_ncu_summary.json",
+               "ipc_per_sm": float(summ["sm__inst_executed.avg.per_cycle_elapsed"][0]),
+               "issue_slots_busy_pct": float(summ["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+               "alu_pipe_pct": float(summ["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"][0]),
+               "fma_pipe_pct": float(summ["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"][0]),
+               "dram_pct": float(summ["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"][0])}
+    except Exception:
+        pass
     out = {
         "metric": "OPD leaf-expansions/sec on highway-v0 (HighwayLite)", "value": value, "unit": "expansions/s",
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
@@ -320,7 +332,7 @@ def run_b200(a):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "opd_highway_kernel",
-                     "bytes_per_expansion": bytes_per_exp,
+                     "bytes_per_expansion": bytes_per_exp, "limiter": "instruction issue (see ncu)", "ncu": ncu,
                      "note": "latency/FP32-issue bound by construction (15 dependent sub-steps per child); "
                              "HBM fraction reported as the contract asks, see DESIGN.md section 4"},
     }
