@@ -331,7 +331,7 @@ def run_b200(a):
         "gpu_launches": a.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "opd_highway_kernel",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "opd_highway_multi_kernel",
                      "bytes_per_expansion": bytes_per_exp, "limiter": "instruction issue (see ncu)", "ncu": ncu,
                      "note": "latency/FP32-issue bound by construction (15 dependent sub-steps per child); "
                              "HBM fraction reported as the contract asks, see DESIGN.md section 4"},
