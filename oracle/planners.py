@@ -455,3 +455,106 @@ def robust_value_iteration(mode, transitions, rewards, gamma, iterations):
             break
         q = nq
     return q, sweeps
+
+
+# --------------------------------------------------------------------------
+# GBOP-T / state-aware OPD -- rl_agents/agents/tree_search/state_aware.py
+# (oracle groundwork for SURVEY 8f rank 3; no device implementation yet)
+# --------------------------------------------------------------------------
+def state_aware_plan(env, observation, budget, gamma, np_random, terminal_reward=0.0, backup_aggregated_nodes=True,
+                     prune_suboptimal_leaves=True, accuracy=0):
+    """StateAwarePlanner.plan (state_aware.py:118-130).  Observations must be hashable state ids
+    (the reference keys its tables by str(observation)).  Returns (plan, tree, state_values, leaves)."""
+    t = Tree()
+    t.reward, t.lower, t.done, t.obs = [], [], [], []
+    states = []
+    state_nodes = {}                      # observation -> node ids in creation order (:20-22)
+    default_value = 1 / (1 - gamma)
+    state_values = {}
+
+    def sv(o):
+        return state_values.get(o, default_value)
+
+    def update_value(o, value):           # :104-116
+        delta = sv(o) - value
+        if delta > 0:
+            state_values[o] = value
+        elif o not in state_values:
+            state_values[o] = default_value          # defaultdict access materialises the key
+        return delta
+
+    def upper(i):                         # get_value_upper_bound (:66-68)
+        return t.lower[i] + (gamma ** t.depth[i]) * sv(t.obs[i])
+
+    def new_node(parent, action, depth, state):
+        t.parent.append(parent); t.action.append(action); t.depth.append(depth); t.count.append(1)
+        t.first_child.append(-1); t.n_children.append(0)
+        t.reward.append(0.0); t.lower.append(0.0); t.done.append(False); t.obs.append(None)
+        states.append(state)
+        return len(t.parent) - 1
+
+    root = new_node(-1, -1, 0, env)
+    t.obs[root] = observation
+    state_nodes[observation] = [root]
+    state_values[observation] = default_value
+    leaves = [root]
+    for _ in range(int(budget) // env.action_space.n):
+        best = leaves[0]                                    # run(): first max (:92)
+        for i in leaves[1:]:
+            if upper(i) > upper(best):
+                best = i
+        leaves.remove(best)                                 # expand (deterministic.py:28-43)
+        actions = _available_actions(states[best])
+        t.first_child[best] = len(t.parent)
+        t.n_children[best] = len(actions)
+        d = t.depth[best] + 1
+        for a in actions:
+            c = new_node(best, a, d, copy.deepcopy(states[best]))
+            obs, reward, done, _, _ = states[c].step(a)
+            leaves.append(c)
+            if not (0 <= reward <= 1):
+                raise ValueError("This planner assumes that all rewards are normalized in [0, 1]")
+            t.reward[c] = reward
+            t.done[c] = bool(done)
+            t.lower[c] = t.lower[best] + (gamma ** (d - 1)) * reward
+            if done:
+                t.lower[c] = t.lower[c] + terminal_reward * (gamma ** d) / (1 - gamma)
+            n = c
+            while n >= 0:
+                t.count[n] += 1
+                n = t.parent[n]
+            t.obs[c] = obs                                  # StateAwareNode.update (:15-26)
+            state_nodes.setdefault(obs, []).append(c)
+            if done:
+                update_value(obs, 0)
+        states[best] = None
+        queue = [best]                                      # backup_to_root (:42-64)
+        while queue:
+            node = queue.pop(0)
+            delta = 0
+            if t.n_children[node] > 0:
+                kids = list(t.children(node))
+                bc = kids[0]
+                for c in kids[1:]:
+                    if upper(c) > upper(bc):
+                        bc = c
+                backup = t.reward[bc] + gamma * sv(t.obs[bc])
+                if t.obs[bc] not in state_values:
+                    state_values[t.obs[bc]] = default_value
+                delta = update_value(t.obs[node], backup)
+            for nb in state_nodes[t.obs[node]]:
+                if t.parent[nb] >= 0 and (nb == node or backup_aggregated_nodes) and \
+                        delta > accuracy * (1 - gamma) * gamma ** (t.depth[nb] - 1):
+                    queue.append(t.parent[nb])
+        if prune_suboptimal_leaves:                         # :98-99, prune (:28-40)
+            for leaf in reversed(list(leaves)):
+                ub = upper(leaf)
+                for node in state_nodes[t.obs[leaf]]:
+                    if node != leaf and upper(node) >= ub and t.depth[node] >= t.depth[leaf] and \
+                            (t.n_children[node] > 0 or node in leaves):
+                        leaves.remove(leaf)
+                        break
+    # StateAwarePlanner.plan calls super().plan() -- which already runs get_plan() -- and then get_plan()
+    # again (:124,:130): the tie-breaking RNG is consumed twice and the second walk is the one returned
+    greedy_plan(t, t.lower, np_random)
+    return greedy_plan(t, t.lower, np_random), t, state_values, leaves

@@ -241,6 +241,24 @@ def main():
     sub["temperature"] = float(agent.planner.config["temperature"])
     out["mcts_subtree"] = sub
 
+    # ---------------- GBOP-T (state-aware OPD) on finite: oracle groundwork for SURVEY 8f rank 3 ----------------
+    from rl_agents.agents.tree_search.state_aware import StateAwarePlannerAgent
+    gb = {}
+    for key, (bud, gam, seed_) in {"large1_b500_g0.9": (500, 0.9, 0), "large1_b2000_g0.8": (2000, 0.8, 1)}.items():
+        del CREATED[:]
+        _instrument_done = True
+        agent = StateAwarePlannerAgent(finite(), {"budget": bud, "gamma": gam})
+        agent.seed(seed_)
+        plan = agent.plan(0)
+        pl = agent.planner
+        gb[key] = {"budget": bud, "gamma": gam, "seed": seed_, "plan": [int(a) for a in plan],
+                   "state_values": {str(k): float(v) for k, v in pl.state_values.items()},
+                   "n_leaves": len(pl.leaves), "n_states": len(pl.state_nodes),
+                   "root_upper": float(pl.root.get_value_upper_bound()),
+                   "leaf_depth_sum": int(sum(l.depth for l in pl.leaves)),
+                   "leaf_lower_sum": float(sum(l.value_lower for l in pl.leaves))}
+    out["gbopt"] = gb
+
     # ---------------- OLOP (KL) on finite ----------------
     ol = {}
     kl_cfg = {"budget": 200, "gamma": 0.9, "continuation_type": "uniform",

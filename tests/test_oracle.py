@@ -105,6 +105,21 @@ def test_reroot_arrays_equals_oracle_reroot():
             canonical_tree(out["first_child"], (out["meta"] >> 8) & 0xff, [out["count"].tolist()])
 
 
+@pytest.mark.parametrize("key", sorted(G.get("gbopt", {})))
+def test_state_aware_planner_gbopt(key):
+    """Oracle groundwork for SURVEY 8f rank 3 (no device implementation yet): the flat restatement of
+    StateAwarePlanner equals the reference (plan, state-value table, frontier after pruning)."""
+    g = G["gbopt"][key]
+    plan, t, state_values, leaves = planners.state_aware_plan(finite(), 0, g["budget"], g["gamma"], np_random(g["seed"]))
+    assert plan == g["plan"]
+    default = 1 / (1 - g["gamma"])      # the reference's defaultdict also materialises keys it merely reads
+    assert all(state_values.get(int(k), default) == v for k, v in g["state_values"].items())
+    assert all(str(k) in g["state_values"] for k in state_values)
+    assert len(leaves) == g["n_leaves"] and len({o for o in t.obs}) == g["n_states"]
+    assert sum(t.depth[l] for l in leaves) == g["leaf_depth_sum"]
+    assert sum(t.lower[l] for l in leaves) == g["leaf_lower_sum"]
+
+
 @pytest.mark.parametrize("key", sorted(G["olop"]))
 def test_olop_finite(key):
     g = G["olop"][key]
