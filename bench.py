@@ -26,9 +26,19 @@ sys.path.insert(0, ROOT)
 
 BUDGET = 10000
 GAMMA = 0.8
+C2_WORKLOAD = ("C2: DeterministicPlannerAgent (OPD) plan() on HighwayLite (highway-v0 stand-in, 16 vehicles, "
+               "15 sub-steps/step), budget %d, gamma %g")
 N_ACTIONS = 5
 STATE_BYTES = 136 * 4
 NODE_BYTES = 5 * 4 + 3 * 8          # parent, first_child, depth, count, meta + reward, lower, upper
+
+
+def bench_config(a):
+    """`config` of the JSON line: identical for the GPU arm and the --impl reference arm."""
+    return {"workload": C2_WORKLOAD % (a.budget, a.gamma), "budget": a.budget, "gamma": a.gamma,
+            "env": "HighwayLite", "n_actions": N_ACTIONS, "expansions_per_plan": a.budget // N_ACTIONS,
+            "unit_of_work": "DeterministicNode.expand() calls (deterministic.py:28-43), strict best-first per tree",
+            "l2": "GPU arm: thousands of independent decisions per step, tree arenas >> 126 MB L2 (no flush needed)"}
 
 
 def parse():
@@ -42,7 +52,9 @@ def parse():
     ap.add_argument("--gamma", type=float, default=GAMMA)
     ap.add_argument("--keys-in-smem", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="OPD batch kernel variant (b2_opd_config.reserved)")
-    ap.add_argument("--cpu-budget", type=int, default=2500, help="budget of the bounded CPU sample")
+    ap.add_argument("--cpu-box", type=float, default=20.0, help="time box (s) of the single-core CPU sample")
+    ap.add_argument("--ref-plans", type=int, default=2, help="--impl reference: whole plan()s per process in the timed steps")
+    ap.add_argument("--ref-time-box", type=float, default=420.0, help="--impl reference: stop after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -97,81 +109,244 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's plan() (reference/oracle is pure Python)
 # ----------------------------------------------------------------------------
-def _cpu_plan(args):
-    seed, budget, gamma = args
+def usable_cores():
+    """Host threads this process may really use: the affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the lease)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                       # cgroup v2
+            q, period = f.read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(period)
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:      # cgroup v1
+                q = float(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                period = float(f.read())
+            if q > 0:
+                quota = q / period
+        except Exception:
+            pass
+    if quota is not None:
+        n = min(n, max(1, int(quota + 0.5)))
+    return max(1, n)
+
+
+def _spin(seconds):
+    """busy loop; returns iterations per second (probe of the cores that really run in parallel)."""
+    t0 = time.perf_counter()
+    n = 0
+    x = 0
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(20000):
+            x += 1
+        n += 1
+    return n / (time.perf_counter() - t0)
+
+
+def effective_workers(cores):
+    """`cores` processes spinning together vs one alone: leases that advertise more threads than they
+    schedule show up as a per-process slowdown; the pool is sized to what runs in parallel."""
+    import multiprocessing as mp
+    if cores <= 1:
+        return 1
+    solo = _spin(0.3)
+    with mp.Pool(cores) as pool:
+        pool.map(_spin, [0.05] * cores)
+        rates = pool.map(_spin, [0.5] * cores)
+    par = sum(rates) / solo
+    return max(1, min(cores, int(par + 0.5)))
+
+
+class _Stop(Exception):
+    pass
+
+
+def cpu_baseline(budget, gamma, box_s=20.0):
+    """The oracle port's plan() (single core, as the reference planner is single-threaded Python) at the
+    bench budget, time-boxed: expand() calls completed in `box_s` seconds of one plan()."""
     import numpy as np
     from oracle import envs as oenvs
     from oracle import planners
-    t0 = time.perf_counter()
-    _, t = planners.opd_plan(oenvs.HighwayLite(seed=seed), budget, gamma,
-                             np_random=np.random.Generator(np.random.PCG64(np.random.SeedSequence(0))))
-    return budget // N_ACTIONS, time.perf_counter() - t0
+    st = {"n": 0, "t0": 0.0, "dt": 0.0}
+
+    def tick():
+        st["n"] += 1
+        st["dt"] = time.perf_counter() - st["t0"]
+        if st["dt"] > box_s:
+            raise _Stop()
+
+    env = oenvs.HighwayLite(seed=0)
+    st["t0"] = time.perf_counter()
+    try:
+        planners.opd_plan(env, budget, gamma, np_random=np.random.Generator(np.random.PCG64(np.random.SeedSequence(0))),
+                          on_expansion=tick)
+        done = "whole plan()"
+    except _Stop:
+        done = "first %d of %d expansions (time box %.0f s; later expansions are slower: the frontier scan is O(n))" \
+               % (st["n"], budget // N_ACTIONS, box_s)
+    return {"value": st["n"] / st["dt"], "unit": "expansions/s", "cores": 1, "kind": "port",
+            "sample": "oracle.planners.opd_plan on HighwayLite seed 0, budget %d: %s, %.1f s" % (budget, done, st["dt"])}
 
 
-def cpu_baseline(budget, gamma):
-    """One plan() of the oracle port (single core, as the reference planner is
-    single-threaded Python) on the bounded sample `budget`."""
-    n_exp, dt = _cpu_plan((0, budget, gamma))
-    return {"value": n_exp / dt, "unit": "expansions/s", "cores": 1, "kind": "port",
-            "sample": "1 plan() of oracle.planners.opd_plan on HighwayLite seed 0, budget %d (%d expansions, %.1f s)"
-                      % (budget, n_exp, dt)}
-
-
-def cpu_port_c(budget, gamma):
+def cpu_port_c(budget, gamma, cores=None):
     """The C restatement (oracle/c: same spec, literal O(V^2) scans, heap frontier) on one core and on all
-    host threads -- what an optimised CPU implementation of the same path does, next to the Python port."""
+    usable host threads -- what an optimised CPU implementation of the same path does, next to the Python port."""
     from concurrent.futures import ThreadPoolExecutor
-    import numpy as np
     from oracle import c_oracle
     from oracle import envs as oenvs
-    scenes = [oenvs.make_highway_state(s).pack() for s in range(2 * (os.cpu_count() or 1))]
+    cores = cores or usable_cores()
+    scenes = [oenvs.make_highway_state(s).pack() for s in range(4 * cores)]
     c_oracle.opd_plan(scenes[0], 500, gamma)
     t0 = time.perf_counter()
     c_oracle.opd_plan(scenes[0], budget, gamma)
     single = (budget // N_ACTIONS) / (time.perf_counter() - t0)
-    cores = os.cpu_count() or 1
     t0 = time.perf_counter()
     with ThreadPoolExecutor(cores) as ex:
         list(ex.map(lambda w: c_oracle.opd_plan(w, budget, gamma), scenes))
     multi = len(scenes) * (budget // N_ACTIONS) / (time.perf_counter() - t0)
-    return {"value": multi, "unit": "expansions/s", "cores": cores, "single_core_value": single, "kind": "port",
+    return {"value": multi, "unit": "expansions/s", "cores": cores, "os_cpu_count": os.cpu_count(),
+            "single_core_value": single, "kind": "port",
             "sample": "oracle/c OPD, HighwayLite, budget %d (full C2 budget): 1 plan() on one core; %d plan()s on %d threads"
                       % (budget, len(scenes), cores)}
 
 
+def _ref_worker(conn, rank, budget, gamma, bounds):
+    """One reference-arm process: runs budget-`budget` plan()s of the oracle port back to back and stops at
+    the cumulative expansion counts in `bounds` (a step boundary) until the parent says go."""
+    import numpy as np
+    from oracle import envs as oenvs
+    from oracle import planners
+    st = {"n": 0, "k": 0, "plans": [], "t_plan": 0.0}
+
+    n_exp = budget // N_ACTIONS
+
+    def tick():
+        st["n"] += 1
+        if st["n"] % n_exp == 0:            # a whole plan() is done (its greedy get_plan is negligible)
+            now = time.perf_counter()
+            st["plans"].append(now - st["t_plan"])
+            st["t_plan"] = now
+        if st["k"] < len(bounds) and st["n"] >= bounds[st["k"]]:
+            st["k"] += 1
+            conn.send(("step", st["n"], list(st["plans"])))
+            if conn.recv() != "go":
+                raise _Stop()
+
+    try:
+        if conn.recv() != "go":
+            return
+        seed = rank
+        while st["k"] < len(bounds):
+            st["t_plan"] = time.perf_counter()
+            planners.opd_plan(oenvs.HighwayLite(seed=seed), budget, gamma,
+                              np_random=np.random.Generator(np.random.PCG64(np.random.SeedSequence(0))),
+                              on_expansion=tick)
+            seed += 1000
+    except _Stop:
+        pass
+    finally:
+        conn.close()
+
+
 def run_reference(a):
-    """--impl reference: oracle port on all host cores, one plan() per process."""
+    """--impl reference: the oracle port of the reference's plan() (Python, like the reference) on every
+    host core this lease really schedules, at the SAME budget / gamma / env as the GPU arm.  A step is a
+    bounded slice of the workers' plan()s: the K timed steps cover exactly `plans_per_worker` whole
+    plan()s per worker, the W warm-up steps the first part of a discarded plan()."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    budget = a.cpu_budget
-    pool = mp.Pool(cores)
-    try:
-        pool.map(_cpu_plan, [(s, 200, a.gamma) for s in range(cores)])           # spin-up (imports), untimed
-        for w in range(min(a.warmup, 1)):
-            pool.map(_cpu_plan, [(1000 + w * cores + s, budget, a.gamma) for s in range(cores)])
-        t0 = time.perf_counter()
-        total = 0
-        for k in range(a.steps):
-            out = pool.map(_cpu_plan, [(k * cores + s, budget, a.gamma) for s in range(cores)])
-            total += sum(n for n, _ in out)
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    cores = usable_cores()
+    workers = effective_workers(cores)
+    n_exp = a.budget // N_ACTIONS
+    steps, warmup = max(a.steps, 1), max(a.warmup, 0)
+    # size: the port does ~40-55 expand()/s per core at this budget => one plan() ~ 40-50 s
+    plans_per_worker = max(1, int(a.ref_plans))
+    timed = [int(round((k + 1) * plans_per_worker * n_exp / float(steps))) for k in range(steps)]
+    warm_slice = max(1, min(n_exp // max(warmup, 1), 40))
+    ctx = mp.get_context("fork")
+
+    def launch(bounds):
+        procs = []
+        for w in range(workers):
+            pc, cc = ctx.Pipe()
+            p = ctx.Process(target=_ref_worker, args=(cc, w, a.budget, a.gamma, bounds), daemon=True)
+            p.start()
+            cc.close()
+            procs.append((p, pc))
+        return procs
+
+    def stop(procs):
+        for p, pc in procs:
+            try:
+                pc.send("stop")
+            except Exception:
+                pass
+        for p, pc in procs:
+            p.join(2.0)
+            if p.is_alive():
+                p.terminate()
+
+    # warm-up: W short slices of a plan() that is then discarded (imports, allocator, caches)
+    if warmup:
+        procs = launch([warm_slice * (k + 1) for k in range(warmup)])
+        for _ in range(warmup):
+            for p, pc in procs:
+                pc.send("go")
+            for p, pc in procs:
+                pc.recv()
+        stop(procs)
+    procs = launch(timed)
+    t_box = float(a.ref_time_box)
+    done_steps, plan_times, total = 0, [], 0
+    t0 = time.perf_counter()
+    for k in range(steps):
+        for p, pc in procs:
+            pc.send("go")
+        counts = []
+        for p, pc in procs:
+            _, n, plans = pc.recv()
+            counts.append(n)
+            if k == steps - 1:
+                plan_times.extend(plans)
+        done_steps, total = k + 1, sum(counts)
         dt = time.perf_counter() - t0
-    finally:
-        pool.close()
+        if dt > t_box and k + 1 < steps:
+            for p, pc in procs:
+                try:
+                    pc.send("go")
+                    _, _, plans = pc.recv()
+                except Exception:
+                    plans = []
+            break
+    dt = time.perf_counter() - t0
+    stop(procs)
     value = total / dt
-    sample = ("%d processes x 1 plan() per step of the oracle port (oracle.planners.opd_plan, HighwayLite, "
-              "budget %d = %d expansions each; the reference is O(budget^2), full budget %d is slower per expansion)"
-              % (cores, budget, budget // N_ACTIONS, a.budget))
+    plan_times.sort()
+    med = plan_times[len(plan_times) // 2] if plan_times else None
+    sample = ("%d processes (usable cores %d, os.cpu_count %d), each running whole plan()s of the oracle port "
+              "(oracle.planners.opd_plan = the reference's algorithm in Python, HighwayLite) at budget %d (%d expand() "
+              "each) back to back; %d of %d timed steps done = %d expansions in %.1f s; 1 step = 1/%d of %d plan()s per "
+              "process" % (workers, cores, os.cpu_count() or 0, a.budget, n_exp, done_steps, steps, total, dt, steps,
+                           plans_per_worker))
     print(json.dumps({
         "impl": "reference", "metric": "OPD leaf-expansions/sec on highway-v0 (HighwayLite)", "value": value,
-        "unit": "expansions/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * dt / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "unit": "expansions/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "steps_done": done_steps,
+        "ms_per_step": 1e3 * dt / max(done_steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "OPD plan() on HighwayLite (highway-v0 stand-in), gamma %g, CPU sample budget %d"
-                               % (a.gamma, budget), "budget": budget, "gamma": a.gamma},
-        "cpu_baseline": {"value": value, "unit": "expansions/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(a),
+        "cpu_baseline": {"value": value, "unit": "expansions/s", "cores": workers, "kind": "port", "sample": sample,
+                         "single_process_median_plan_s": med,
+                         "single_process_value": (n_exp / med) if med else None,
+                         "plans_timed": len(plan_times)},
         "e2e": {"value": value, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -316,15 +491,13 @@ def run_b200(a):
         "metric": "OPD leaf-expansions/sec on highway-v0 (HighwayLite)", "value": value, "unit": "expansions/s",
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: DeterministicPlannerAgent (OPD) on HighwayLite (highway-v0 stand-in, 16 vehicles, "
-                               "15 sub-steps/step), budget %d, gamma %g, %d independent decisions per GPU per step, "
-                               "strict best-first per tree" % (a.budget, a.gamma, trees),
-                   "budget": a.budget, "gamma": a.gamma, "trees_per_gpu": trees, "expansions_per_tree": n_exp,
-                   "mean_children_per_expansion": mean_children, "child_nodes_per_s": value * mean_children,
-                   "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)"
-                         % (trees * capacity * (STATE_BYTES + NODE_BYTES) / 1e9),
-                   "parallelism": "trees sharded over %d GPU(s), no data-path collective" % world,
-                   "keys_in_smem": bool(a.keys_in_smem)},
+        "config": bench_config(a),
+        "run_config": {"trees_per_gpu": trees, "expansions_per_tree": n_exp,
+                       "mean_children_per_expansion": mean_children, "child_nodes_per_s": value * mean_children,
+                       "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)"
+                             % (trees * capacity * (STATE_BYTES + NODE_BYTES) / 1e9),
+                       "parallelism": "trees sharded over %d GPU(s), no data-path collective" % world,
+                       "keys_in_smem": bool(a.keys_in_smem)},
         "e2e": {"value": e2e_value, "unit": "expansions/s", "h2d_bytes_per_step": int(trees * STATE_BYTES),
                 "d2h_bytes_per_step": int(plan_host.numel() + res_host.numel() * 4), "ms_per_step": ms_e2e / a.steps,
                 "path": "b2_opd_plan_host (C ABI, host buffers, synchronous); wall clock over the steps, max over ranks"},
@@ -337,7 +510,7 @@ def run_b200(a):
                              "HBM fraction reported as the contract asks, see DESIGN.md section 4"},
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(a.cpu_budget, a.gamma)
+        out["cpu_baseline"] = cpu_baseline(a.budget, a.gamma, a.cpu_box)
         try:
             out["cpu_port_c"] = cpu_port_c(a.budget, a.gamma)
         except Exception as e:      # the C oracle is optional test infrastructure

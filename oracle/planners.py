@@ -42,9 +42,10 @@ class Tree(object):
 # --------------------------------------------------------------------------
 # OPD -- rl_agents/agents/tree_search/deterministic.py
 # --------------------------------------------------------------------------
-def opd_plan(env, budget, gamma, terminal_reward=0.0, np_random=None):
+def opd_plan(env, budget, gamma, terminal_reward=0.0, np_random=None, on_expansion=None):
     """OptimisticDeterministicPlanner.plan (deterministic.py:116-122) after a
-    reset (deterministic.py:102-104).  Returns (plan, tree)."""
+    reset (deterministic.py:102-104).  Returns (plan, tree).  `on_expansion` (bench.py's
+    time-boxed CPU arm) is called after every expand(); it does not touch the search."""
     t = Tree()
     t.reward, t.lower, t.upper, t.done = [], [], [], []
     states = []
@@ -105,6 +106,8 @@ def opd_plan(env, budget, gamma, terminal_reward=0.0, np_random=None):
             t.lower[n] = max(t.lower[c] for c in t.children(n))
             t.upper[n] = max(t.upper[c] for c in t.children(n))
             n = t.parent[n]
+        if on_expansion is not None:
+            on_expansion()
     t.terminal_expansions = terminal_expansions
     t.n_leaves = len(leaves)
     return greedy_plan(t, t.lower, np_random), t
