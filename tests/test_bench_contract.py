@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
-                        "--warmup", "0", "--cpu-budget", "60"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                        "--warmup", "1", "--budget", "60", "--ref-plans", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                        timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.strip()]
