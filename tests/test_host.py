@@ -140,3 +140,71 @@ def test_finite_env_steps_like_the_oracle_env():
     for _ in range(50):
         act = int(rng.integers(5))
         assert a.step(act) == b.step(act)
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference tree not present")
+@pytest.mark.parametrize("receding_horizon", [1, 2, 3, 5])
+def test_receding_horizon_schedule_matches_the_reference_agent(receding_horizon):
+    """The agent shell (own implementation) against the reference's AbstractTreeSearchAgent driven by the
+    same scripted planner: identical plan() outputs, planner calls and step_tree arguments."""
+    ref_loader.load_reference()
+    from rl_agents.agents.tree_search.abstract import AbstractTreeSearchAgent as RefAgent
+    from rl_agents_b200.agents.tree_search.abstract import AbstractTreeSearchAgent as OurAgent
+
+    lengths = [4, 1, 3, 2, 6, 1, 1, 5, 3]
+
+    class Scripted(object):
+        def __init__(self, env, config):
+            self.log, self.k = [], 0
+
+        def plan(self, state, observation):
+            n = lengths[self.k % len(lengths)]
+            self.k += 1
+            self.log.append(("plan", observation))
+            return [10 * self.k + i for i in range(n)]
+
+        def step_tree(self, actions):
+            self.log.append(("step", list(actions)))
+
+        def step_by_reset(self):
+            self.log.append(("reset",))
+
+        def seed(self, seed=None):
+            return [seed]
+
+    class Env(object):
+        unwrapped = property(lambda self: self)
+
+    def run(cls):
+        class A(cls):
+            PLANNER_TYPE = Scripted
+        a = A(Env(), {"receding_horizon": receding_horizon})
+        outs = []
+        for t in range(25):
+            if t == 13:
+                a.reset()
+            outs.append(list(a.plan(t)))
+        return outs, a.planner.log, a.config
+
+    ours, ref = run(OurAgent), run(RefAgent)
+    assert ours[0] == ref[0] and ours[1] == ref[1]
+    assert ours[2] == ref[2]
+
+
+def test_preprocess_env_applies_methods_in_sequence():
+    from rl_agents_b200.agents.common.factory import _apply, preprocess_env
+
+    class E(object):
+        def __init__(self, tag=""):
+            self.tag = tag
+        unwrapped = property(lambda self: self)
+
+        def simplify(self):
+            return E(self.tag + "s")
+
+        def change(self, args):
+            return E(self.tag + "c%d" % args)
+
+    out = preprocess_env(E(), [{"method": "simplify"}, {"method": "change", "args": 3}, {"method": "missing"}, {"args": 1}])
+    assert out.tag == "sc3"
+    assert _apply(E("x"), {"method": "nope"}).tag == "x"
