@@ -129,6 +129,8 @@ typedef struct b2_opd_config {
     const double* gamma_pow;     /* [n_expansions+2] gamma**d   (host floats) */
     const double* gamma_pow_div; /* [n_expansions+2] gamma**d / (1 - gamma)   */
     b2_finite_mdp mdp;      /* env_kind == FINITE                            */
+    const double* terminal_bonus;/* [n_expansions+2] (terminal_reward * gamma**d) / (1 - gamma), the
+                                    reference's association (:60-63), host floats */
 } b2_opd_config;
 
 /* Node arrays, each [n_trees, node_capacity] (struct-of-arrays in HBM) */
@@ -161,6 +163,37 @@ int64_t b2_opd_workspace_bytes(const b2_opd_config* cfg);
  * [n_trees, B2_OPD_RESULT_WORDS]. */
 int b2_opd_plan(const b2_opd_config* cfg, const int32_t* root_states, const b2_opd_tree* tree,
                 void* workspace, int8_t* plan, int32_t* result, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Wavefront OPD: ONE decision searched by the whole GPU.  Per wave the
+ * k = min(width, expansions left, frontier size) best leaves -- in the
+ * reference's arg-max order (value_upper descending, node id ascending,
+ * deterministic.py:110) -- are expanded in increasing node-id order and all their
+ * children simulated at once.  width = 1 is the reference's algorithm
+ * (deterministic.py:106-122); for any width the result is bit-identical with the
+ * specification oracle/planners.py::opd_plan_wavefront.
+ * ---------------------------------------------------------------------- */
+typedef struct b2_opd_wave_config {
+    int32_t env_kind;       /* B2_ENV_*                                      */
+    int32_t n_actions;      /* action_space.n (:118)                         */
+    int32_t n_expansions;   /* budget // n_actions (:118)                    */
+    int32_t node_capacity;  /* >= 1 + n_expansions * n_actions, < 2^28       */
+    int32_t plan_capacity;
+    int32_t width;          /* leaves expanded per wave (>= 1)               */
+    int32_t max_ctas;       /* 0: one CTA per SM                             */
+    int32_t reserved;
+    const double* gamma_pow;      /* [n_expansions+2] gamma**d               */
+    const double* gamma_pow_div;  /* [n_expansions+2] gamma**d / (1 - gamma) */
+    const double* terminal_bonus; /* [n_expansions+2] terminal_reward * gamma**d / (1 - gamma) (:60-63) */
+    b2_finite_mdp mdp;
+} b2_opd_wave_config;
+
+int64_t b2_opd_wave_workspace_bytes(const b2_opd_wave_config* cfg);
+/* tree: node arrays of ONE tree ([node_capacity] each, state [node_capacity(,136)]); root_state: [1] state id
+ * or [136] words; plan: int8 [plan_capacity]; result: int32 [B2_OPD_RESULT_WORDS] as for b2_opd_plan, plus
+ * [7] number of waves.  Cooperative launch on `stream` (one CTA per SM). */
+int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* root_state, const b2_opd_tree* tree,
+                     void* workspace, int8_t* plan, int32_t* result, void* stream);
 
 /* Host-buffer convenience API (callers that do not manage CUDA memory: plain C, cgo, JNI ...).
  * A handle owns the device arena of a batch of trees; *_host pointers are ordinary host memory

@@ -97,6 +97,76 @@ int opd_highway_plan(const int32_t* root_words, int budget, double gamma, double
     return n;
 }
 
+static int cmp_int(const void* a, const void* b) { return *(const int32_t*)a - *(const int32_t*)b; }
+
+/* SPECIFICATION of the wavefront OPD (oracle/planners.py::opd_plan_wavefront, same statement in C): per wave
+ * the k = min(width, expansions left, frontier size) best leaves by (upper desc, id asc) are expanded in
+ * increasing id order; counts and backups bottom-up afterwards.  width = 1 is opd_highway_plan. */
+int opd_highway_plan_wave(const int32_t* root_words, int budget, double gamma, double terminal_reward, int width,
+                          int32_t* parent, int32_t* action, int32_t* depth, int32_t* count, int32_t* first_child,
+                          int32_t* n_children, int32_t* done, double* reward, double* lower, double* upper,
+                          int32_t* n_leaves, int32_t* n_waves) {
+    const int n_exp = budget / 5, cap = 1 + n_exp * 5;
+    opd_tree t = {parent, action, depth, count, first_child, n_children, done, reward, lower, upper};
+    hl_state* states = (hl_state*)malloc((size_t)cap * sizeof(hl_state));
+    int32_t* heap = (int32_t*)malloc((size_t)cap * sizeof(int32_t));
+    int32_t* chosen = (int32_t*)malloc((size_t)(width > 0 ? width : 1) * sizeof(int32_t));
+    int heap_n = 0, n = 1, remaining = n_exp, waves = 0;
+    memcpy(&states[0], root_words, sizeof(hl_state));
+    parent[0] = -1; action[0] = -1; depth[0] = 0; count[0] = 1; first_child[0] = -1; n_children[0] = 0; done[0] = 0;
+    reward[0] = lower[0] = upper[0] = 0.0;
+    heap_push(&t, heap, &heap_n, 0);
+    while (remaining > 0) {
+        int k = width < remaining ? width : remaining;
+        if (k > heap_n) k = heap_n;
+        for (int j = 0; j < k; ++j) chosen[j] = heap_pop(&t, heap, &heap_n);
+        qsort(chosen, (size_t)k, sizeof(int32_t), cmp_int);
+        for (int j = 0; j < k; ++j) {
+            const int leaf = chosen[j];
+            int acts[5];
+            const int na = hl_available_actions(&states[leaf], acts);
+            first_child[leaf] = n;
+            n_children[leaf] = na;
+            const int d = depth[leaf] + 1;
+            for (int q = 0; q < na; ++q) {
+                const int c = n++;
+                states[c] = states[leaf];
+                int flags;
+                const double r = (double)hl_step(&states[c], acts[q], &flags);
+                if (!(r >= 0.0 && r <= 1.0)) { free(states); free(heap); free(chosen); return -1; }
+                parent[c] = leaf; action[c] = acts[q]; depth[c] = d; count[c] = 1; first_child[c] = -1; n_children[c] = 0;
+                done[c] = flags & 1;
+                reward[c] = r;
+                lower[c] = lower[leaf] + pow(gamma, d - 1) * r;
+                upper[c] = lower[c] + pow(gamma, d) / (1 - gamma);
+                if (done[c]) { lower[c] = lower[c] + terminal_reward * pow(gamma, d) / (1 - gamma); upper[c] = lower[c]; }
+                heap_push(&t, heap, &heap_n, c);
+            }
+        }
+        remaining -= k;
+        ++waves;
+    }
+    for (int c = n - 1; c > 0; --c)
+        for (int a = c; a >= 0; a = parent[a]) count[a] += 1;
+    for (int p = n - 1; p >= 0; --p) {
+        if (!n_children[p]) continue;
+        double lo = lower[first_child[p]], up = upper[first_child[p]];
+        for (int q = 1; q < n_children[p]; ++q) {
+            const int c = first_child[p] + q;
+            if (lower[c] > lo) lo = lower[c];
+            if (upper[c] > up) up = upper[c];
+        }
+        lower[p] = lo;
+        upper[p] = up;
+    }
+    *n_leaves = heap_n;
+    *n_waves = waves;
+    free(states);
+    free(heap);
+    free(chosen);
+    return n;
+}
+
 /* batched env steps (for parity tests of the env alone) */
 void hl_step_batch(int32_t* words, const int32_t* actions, float* rewards, int32_t* flags, int n) {
     for (int i = 0; i < n; ++i) rewards[i] = hl_step((hl_state*)(words + (size_t)i * HL_WORDS), actions[i], &flags[i]);

@@ -25,6 +25,7 @@ def load():
         build()
         _lib = ctypes.CDLL(LIB)
         _lib.opd_highway_plan.restype = ctypes.c_int
+        _lib.opd_highway_plan_wave.restype = ctypes.c_int
         _lib.mcts_highway_plan.restype = ctypes.c_int
     return _lib
 
@@ -61,6 +62,27 @@ def opd_plan(root_words, budget, gamma, terminal_reward=0.0):
         raise ValueError("This planner assumes that all rewards are normalized in [0, 1]")
     out = {k: v[:n] for k, v in {**i32, **f64}.items()}
     out["n_leaves"] = n_leaves.value
+    return out
+
+
+def opd_plan_wave(root_words, budget, gamma, width, terminal_reward=0.0):
+    """The wavefront specification (oracle.planners.opd_plan_wavefront) in C; same dict as opd_plan + n_waves."""
+    lib = load()
+    cap = 1 + (int(budget) // 5) * 5
+    i32 = {k: np.zeros(cap, dtype=np.int32) for k in ("parent", "action", "depth", "count", "first_child",
+                                                      "n_children", "done")}
+    f64 = {k: np.zeros(cap, dtype=np.float64) for k in ("reward", "lower", "upper")}
+    n_leaves, n_waves = ctypes.c_int32(0), ctypes.c_int32(0)
+    root = np.ascontiguousarray(root_words, dtype=np.int32)
+    n = lib.opd_highway_plan_wave(_p(root), ctypes.c_int(int(budget)), ctypes.c_double(gamma),
+                                  ctypes.c_double(terminal_reward), ctypes.c_int(int(width)),
+                                  _p(i32["parent"]), _p(i32["action"]), _p(i32["depth"]), _p(i32["count"]),
+                                  _p(i32["first_child"]), _p(i32["n_children"]), _p(i32["done"]), _p(f64["reward"]),
+                                  _p(f64["lower"]), _p(f64["upper"]), ctypes.byref(n_leaves), ctypes.byref(n_waves))
+    if n < 0:
+        raise ValueError("This planner assumes that all rewards are normalized in [0, 1]")
+    out = {k: v[:n] for k, v in {**i32, **f64}.items()}
+    out["n_leaves"], out["n_waves"] = n_leaves.value, n_waves.value
     return out
 
 

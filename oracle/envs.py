@@ -12,7 +12,8 @@ no reference test pins any env arithmetic.
 
   FiniteMDPLite  table semantics read by value_iteration.py:51-63 plus
                  `step`: r = R[s,a]; s' = T[s,a] (deterministic) or
-                 s' ~ P[s,a,:]; done = terminal[s'].
+                 s' ~ P[s,a,:]; done = terminal[s] (the state the action is taken
+                 in, as the `finite_mdp` package's MDP.step and value_iteration.py:62 do).
   HighwayLite    docs/HIGHWAY_LITE_SPEC.md -- straight 4-lane highway, one
                  meta-action ego + IDM/MOBIL traffic, 15 physics sub-steps per
                  decision, every operation a single IEEE fp32 op (no FMA) so
@@ -97,7 +98,7 @@ class FiniteMDPLite(object):
         else:
             raise ValueError("Unknown mode")
         m.state = s2
-        return s2, r, bool(m.terminal[s2]), False, {}
+        return s2, r, bool(m.terminal[s]), False, {}
 
 
 class LegacyStepEnv(object):

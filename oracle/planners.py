@@ -113,6 +113,64 @@ def opd_plan(env, budget, gamma, terminal_reward=0.0, np_random=None, on_expansi
     return greedy_plan(t, t.lower, np_random), t
 
 
+def opd_plan_wavefront(env, budget, gamma, width, terminal_reward=0.0, np_random=None):
+    """SPECIFICATION of the device's wavefront OPD (b2_opd_plan_wave), not a reference algorithm: the
+    reference expands ONE leaf per iteration (deterministic.py:106-122); the wavefront takes, per wave,
+    the k = min(width, expansions left, frontier size) best leaves in the order (value_upper descending,
+    node id ascending) -- the reference's own arg-max order, deterministic.py:110 -- and expands them in
+    increasing node-id order (children in action order, ids in creation order).  width = 1 IS the
+    reference's algorithm.  Node bounds, counts and the backup are the reference's (update :45-65,
+    backup_to_root :74-79): they do not depend on the expansion order.  Returns (plan, tree); tree.waves
+    lists the leaves of every wave."""
+    t = Tree()
+    t.reward, t.lower, t.upper, t.done = [0.0], [0.0], [0.0], [False]
+    t.parent, t.action, t.depth, t.count, t.first_child, t.n_children = [-1], [-1], [0], [1], [-1], [0]
+    states = [env]
+    leaves = [0]
+    remaining = int(budget) // env.action_space.n
+    t.waves, t.terminal_expansions = [], 0
+    while remaining > 0:
+        k = min(int(width), remaining, len(leaves))
+        chosen = sorted(sorted(leaves, key=lambda i: (-t.upper[i], i))[:k])
+        t.waves.append(chosen)
+        for best in chosen:
+            t.terminal_expansions += 1 if t.done[best] else 0
+            leaves.remove(best)
+            actions = _available_actions(states[best])
+            t.first_child[best] = len(t.parent)
+            t.n_children[best] = len(actions)
+            d = t.depth[best] + 1
+            for a in actions:
+                st = copy.deepcopy(states[best])
+                _, reward, done, _, _ = st.step(a)
+                if not (0 <= reward <= 1):
+                    raise ValueError("This planner assumes that all rewards are normalized in [0, 1]")
+                lo = t.lower[best] + (gamma ** (d - 1)) * reward
+                up = lo + (gamma ** d) / (1 - gamma)
+                if done:
+                    lo = up = lo + terminal_reward * (gamma ** d) / (1 - gamma)
+                c = len(t.parent)
+                t.parent.append(best); t.action.append(a); t.depth.append(d); t.count.append(1)
+                t.first_child.append(-1); t.n_children.append(0)
+                t.reward.append(reward); t.lower.append(lo); t.upper.append(up); t.done.append(bool(done))
+                states.append(st)
+                leaves.append(c)
+            states[best] = None
+        remaining -= k
+    # counts (:64-65: +1 on self and every ancestor per created node) and backups (:74-79), bottom-up
+    for c in range(len(t.parent) - 1, 0, -1):
+        n = c
+        while n >= 0:
+            t.count[n] += 1
+            n = t.parent[n]
+    for n in range(len(t.parent) - 1, -1, -1):
+        if t.n_children[n]:
+            t.lower[n] = max(t.lower[c] for c in t.children(n))
+            t.upper[n] = max(t.upper[c] for c in t.children(n))
+    t.n_leaves = len(leaves)
+    return greedy_plan(t, t.lower, np_random), t
+
+
 def greedy_plan(t, values, np_random):
     """AbstractPlanner.get_plan (abstract.py:143-156) with
     DeterministicNode.selection_rule (deterministic.py:21-26): arg-max of the

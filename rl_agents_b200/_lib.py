@@ -38,7 +38,15 @@ class OPDConfig(ctypes.Structure):
     _fields_ = [("env_kind", c_int32), ("n_trees", c_int32), ("n_actions", c_int32),
                 ("n_expansions", c_int32), ("node_capacity", c_int32), ("plan_capacity", c_int32),
                 ("keys_in_smem", c_int32), ("reserved", c_int32), ("terminal_reward", c_double),
-                ("gamma_pow", c_void_p), ("gamma_pow_div", c_void_p), ("mdp", FiniteMDP)]
+                ("gamma_pow", c_void_p), ("gamma_pow_div", c_void_p), ("mdp", FiniteMDP),
+                ("terminal_bonus", c_void_p)]
+
+
+class OPDWaveConfig(ctypes.Structure):
+    _fields_ = [("env_kind", c_int32), ("n_actions", c_int32), ("n_expansions", c_int32),
+                ("node_capacity", c_int32), ("plan_capacity", c_int32), ("width", c_int32),
+                ("max_ctas", c_int32), ("reserved", c_int32), ("gamma_pow", c_void_p),
+                ("gamma_pow_div", c_void_p), ("terminal_bonus", c_void_p), ("mdp", FiniteMDP)]
 
 
 class OPDTree(ctypes.Structure):
@@ -84,6 +92,9 @@ EXPORTS = {
     "b2_opd_workspace_bytes": (c_int64, [ctypes.POINTER(OPDConfig)]),
     "b2_opd_plan": (c_int, [ctypes.POINTER(OPDConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
                             c_void_p, c_void_p]),
+    "b2_opd_wave_workspace_bytes": (c_int64, [ctypes.POINTER(OPDWaveConfig)]),
+    "b2_opd_plan_wave": (c_int, [ctypes.POINTER(OPDWaveConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "b2_opd_create": (c_int, [ctypes.POINTER(OPDHostConfig), ctypes.POINTER(c_void_p)]),
     "b2_opd_destroy": (None, [c_void_p]),
     "b2_opd_plan_capacity": (c_int32, [c_void_p]),

@@ -16,7 +16,7 @@ struct b2_opd_handle {
     int8_t* plan;
     int32_t* result;
     int32_t* roots;
-    double *gamma_pow, *gamma_pow_div;
+    double *gamma_pow, *gamma_pow_div, *terminal_bonus;
     int32_t* mdp_T;
     double* mdp_R;
     uint8_t* mdp_term;
@@ -30,7 +30,7 @@ extern "C" void b2_opd_destroy(b2_opd_handle* h) {
     if (!h) return;
     void* ptrs[] = {h->tree.parent, h->tree.first_child, h->tree.depth, h->tree.count, h->tree.meta, h->tree.reward,
                     h->tree.lower, h->tree.upper, h->tree.state, h->workspace, h->plan, h->result, h->roots,
-                    h->gamma_pow, h->gamma_pow_div, h->mdp_T, h->mdp_R, h->mdp_term};
+                    h->gamma_pow, h->gamma_pow_div, h->terminal_bonus, h->mdp_T, h->mdp_R, h->mdp_term};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -40,6 +40,7 @@ extern "C" void b2_opd_destroy(b2_opd_handle* h) {
 extern "C" int b2_opd_create(const b2_opd_host_config* hc, b2_opd_handle** out) {
     B2_REQUIRE(hc && out, "null pointer");
     B2_REQUIRE(hc->n_trees > 0 && hc->n_actions > 0 && hc->budget >= 0, "bad batch / budget");
+    B2_REQUIRE(1 + (int64_t)(hc->budget / hc->n_actions) * hc->n_actions < (int64_t)1 << 31, "budget too large for int32 node ids");
     B2_REQUIRE(hc->gamma >= 0.0 && hc->gamma < 1.0, "gamma must be in [0, 1)");
     b2_opd_handle* h = new b2_opd_handle();
     memset(h, 0, sizeof(*h));
@@ -74,11 +75,15 @@ extern "C" int b2_opd_create(const b2_opd_host_config* hc, b2_opd_handle** out) 
     TRY(B2_ALLOC(h->result, (size_t)c.n_trees * B2_OPD_RESULT_WORDS * 4));
     TRY(B2_ALLOC(h->roots, (size_t)c.n_trees * h->root_words * 4));
     // gamma**d tables: C pow() is what CPython's float ** uses, so the values equal the reference's
-    std::vector<double> gp(c.n_expansions + 2), gd(c.n_expansions + 2);
+    std::vector<double> gp(c.n_expansions + 2), gd(c.n_expansions + 2), tb(c.n_expansions + 2);
     for (int d = 0; d < c.n_expansions + 2; ++d) {
         gp[d] = pow(hc->gamma, (double)d);
         gd[d] = gp[d] / (1.0 - hc->gamma);
+        tb[d] = (hc->terminal_reward * gp[d]) / (1.0 - hc->gamma);      // deterministic.py:60-63
     }
+    TRY(B2_ALLOC(h->terminal_bonus, tb.size() * 8));
+    TRY(B2_CUDA_CHECK(cudaMemcpy(h->terminal_bonus, tb.data(), tb.size() * 8, cudaMemcpyHostToDevice)));
+    c.terminal_bonus = h->terminal_bonus;
     TRY(B2_ALLOC(h->gamma_pow, gp.size() * 8));
     TRY(B2_ALLOC(h->gamma_pow_div, gd.size() * 8));
     TRY(B2_CUDA_CHECK(cudaMemcpy(h->gamma_pow, gp.data(), gp.size() * 8, cudaMemcpyHostToDevice)));

@@ -36,8 +36,8 @@ struct FiniteEnv {
     __device__ __forceinline__ double step(const MctsArgs& a, int action, int li, unsigned gmask, float* gs, bool& term, bool& trunc) {
         const b2_finite_mdp& m = a.cfg.mdp;
         const double r = m.reward[(int64_t)s * m.n_actions + action];
+        term = m.terminal[s] != 0;        // finite_mdp's MDP.step: done = terminal[state BEFORE the transition]
         s = m.transition[(int64_t)s * m.n_actions + action];
-        term = m.terminal[s] != 0;
         trunc = false;
         return r;
     }

@@ -70,8 +70,8 @@ struct OFiniteEnv {
     __device__ __forceinline__ double step(const OlopArgs& a, int action, int li, unsigned gmask, float* gs, bool& term) {
         const b2_finite_mdp& m = a.cfg.mdp;
         const double r = m.reward[(int64_t)s * m.n_actions + action];
+        term = m.terminal[s] != 0;        // done = terminal[state BEFORE the transition]
         s = m.transition[(int64_t)s * m.n_actions + action];
-        term = m.terminal[s] != 0;
         return r;
     }
 };

@@ -108,7 +108,7 @@ __device__ __forceinline__ void commit_expansion(const OpdArgs& a, Tournament& T
         double lo = sh.lower + a.cfg.gamma_pow[d - 1] * r;
         double up = lo + a.cfg.gamma_pow_div[d];
         if (done) {
-            lo = lo + a.cfg.terminal_reward * a.cfg.gamma_pow_div[d];
+            lo = lo + a.cfg.terminal_bonus[d];
             up = lo;
         }
         tr.parent[nb + c] = leaf;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(32) opd_finite_kernel(OpdArgs a) {
         if (lane < A) {   // deterministic.py:36-43 for action `lane`
             const int s2 = m.transition[(int64_t)s * A + lane];
             sh.child_reward[lane] = m.reward[(int64_t)s * A + lane];
-            sh.child_done[lane] = m.terminal[s2];
+            sh.child_done[lane] = m.terminal[s];   // finite_mdp's MDP.step: done = terminal[state BEFORE the transition]
             sh.child_action[lane] = lane;
             a.tree.state[nb + n_nodes + lane] = s2;
         }
@@ -596,7 +596,7 @@ extern "C" int b2_opd_plan(const b2_opd_config* cfg, const int32_t* root_states,
     B2_REQUIRE(cfg->n_actions > 0 && cfg->n_actions <= MAX_BRANCH, "n_actions must be in 1..8");
     B2_REQUIRE((int64_t)cfg->node_capacity >= 1 + (int64_t)cfg->n_expansions * cfg->n_actions, "node_capacity too small");
     B2_REQUIRE(cfg->plan_capacity >= cfg->n_expansions + 1, "plan_capacity too small");
-    B2_REQUIRE(cfg->gamma_pow && cfg->gamma_pow_div, "gamma tables missing");
+    B2_REQUIRE(cfg->gamma_pow && cfg->gamma_pow_div && cfg->terminal_bonus, "gamma tables missing");
     cudaStream_t stream = (cudaStream_t)stream_;
     OpdArgs a;
     a.cfg = *cfg; a.tree = *tree; a.root_states = root_states; a.workspace = (char*)workspace;

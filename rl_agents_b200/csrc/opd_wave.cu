@@ -1,0 +1,529 @@
+// Wavefront OPD: ONE decision searched by the whole GPU (b2_opd_plan_wave).
+//
+// The reference's OptimisticDeterministicPlanner.run (deterministic.py:106-114) expands one leaf per
+// iteration -- a chain of `budget / n_actions` dependent env transitions (28 us each on a B200 for
+// HighwayLite).  The wavefront expands, per wave, the k = min(width, expansions left, frontier size) best
+// leaves in the reference's own arg-max order (value_upper descending, node id ascending, :110), in
+// increasing node-id order, and simulates all their children at once on every SM.  width = 1 is the
+// reference's algorithm; the specification for any width is oracle/planners.py::opd_plan_wavefront, and the
+// kernel is bit-identical with it (node ids, counts, fp64 bounds).
+//
+// One cooperative launch, one CTA per SM, waves separated by two grid barriers:
+//   select (CTA 0)  the k-th largest frontier key by bisection over the order-preserving 64-bit image of
+//                   the fp64 keys staged in shared memory (early exit as soon as a threshold isolates
+//                   exactly k keys), ties at the threshold by lowest node id, ordered compaction, child
+//                   ids by prefix sum of the leaves' available-action counts -> work list
+//   simulate (all)  one 16-lane group per child: parent scene -> hw::step -> child scene, node record and
+//                   frontier key (value_upper) written in place; finite MDPs: one thread per child
+// then CTA 0 runs the bottom-up pass (counts :64-65, backup_to_root :74-79) wave by wave in reverse and the
+// greedy plan walk (abstract.py:143-156).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "highway_lite.cuh"
+
+namespace b2 {
+namespace wave {
+
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int GROUPS = THREADS / 16;
+constexpr int STAGE_CAP = 24576;            // fp64 keys staged in shared memory per tile (192 KB)
+constexpr int MAX_BRANCH = 8;
+
+struct Control {                            // head of the workspace; zeroed by the launch wrapper
+    unsigned bar_count, bar_gen;
+    int n_nodes, n_expanded, wave_children, wave_base, n_waves, stop;
+    int error, max_depth, term_exp, pad;
+};
+
+struct Args {
+    b2_opd_wave_config cfg;
+    b2_opd_tree tree;
+    const int32_t* root_state;
+    Control* ctl;
+    double* keys;          // [node_capacity] value_upper of frontier leaves, -inf otherwise
+    int32_t* exp_order;    // [n_expansions] expanded leaves, wave-major, id order inside a wave
+    int32_t* wave_start;   // [n_expansions + 1]
+    int32_t* work;         // [width * n_actions] leaf | action << 28 for every child of the current wave
+    int8_t* plan;
+    int32_t* result;
+};
+
+__device__ __forceinline__ unsigned long long sortable(double x) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+constexpr unsigned long long ABSENT = 0x000fffffffffffffull;   // image of -inf: not a frontier leaf
+
+__device__ __forceinline__ int ld_cg(const int32_t* p) { return __ldcg(p); }
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+
+// grid-wide barrier (all CTAs are co-resident: cooperative launch).  Data written before it by any CTA is
+// read after it with ld.global.cg (L2) by the others.
+__device__ __forceinline__ void grid_barrier(Control* ctl, unsigned n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned* gen_p = &ctl->bar_gen;
+        const unsigned gen = *gen_p;
+        __threadfence();
+        if (atomicAdd(&ctl->bar_count, 1u) == n_ctas - 1) {
+            ctl->bar_count = 0;
+            __threadfence();
+            atomicAdd(&ctl->bar_gen, 1u);
+        } else {
+            while (*gen_p == gen) {}
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int block_sum(int v, int* red, int slot) {   // red: [2][WARPS]; slot alternates
+    const int w = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) red[slot * WARPS + (threadIdx.x >> 5)] = w;
+    __syncthreads();
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < WARPS; ++i) s += red[slot * WARPS + i];
+    return s;
+}
+
+struct SelShared {
+    int red[4 * WARPS];
+    int scan_a[THREADS], scan_b[THREADS];
+    unsigned long long theta;
+    int k, need_eq, total_children;
+};
+
+// exclusive prefix sums of (a, b) over the block; returns totals through ta/tb
+__device__ __forceinline__ void block_scan2(int a, int b, SelShared& sh, int& ea, int& eb, int& ta, int& tb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int xa = __shfl_up_sync(0xffffffffu, ia, o), xb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += xa; ib += xb; }
+    }
+    if (lane == 31) { sh.scan_a[warp] = ia; sh.scan_b[warp] = ib; }
+    __syncthreads();
+    int wa = 0, wb = 0;
+    ta = 0; tb = 0;
+#pragma unroll
+    for (int i = 0; i < WARPS; ++i) {
+        const int va = sh.scan_a[i], vb = sh.scan_b[i];
+        if (i < warp) { wa += va; wb += vb; }
+        ta += va; tb += vb;
+    }
+    ea = wa + ia - a;
+    eb = wb + ib - b;
+    __syncthreads();
+}
+
+// CTA 0: choose this wave's leaves and lay out their children.  Returns the number of children (0: done).
+__device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* skeys, int n_nodes, int n_expanded) {
+    const int tid = threadIdx.x;
+    const int remaining = a.cfg.n_expansions - n_expanded;
+    const int frontier = n_nodes - n_expanded;
+    const int k = min(min(a.cfg.width, remaining), frontier);
+    if (k <= 0) return 0;
+    const int n_tiles = (n_nodes + STAGE_CAP - 1) / STAGE_CAP;
+    auto stage = [&](int tile) {
+        const int base = tile * STAGE_CAP, n = min(STAGE_CAP, n_nodes - base);
+        __syncthreads();
+        for (int i = tid; i < n; i += THREADS) skeys[i] = sortable(__ldcg(a.keys + base + i));
+        __syncthreads();
+        return n;
+    };
+    // blocked partition of a tile with an odd chunk (conflict-free 8-byte shared loads)
+    auto chunk_of = [&](int n, int& lo, int& hi) {
+        const int c = ((n + THREADS - 1) / THREADS) | 1;
+        lo = min(tid * c, n);
+        hi = min(lo + c, n);
+    };
+    int n0 = stage(0);
+    // ---- bisection on the 64-bit images: largest theta with count(u >= theta) >= k ----
+    unsigned long long lo = ABSENT + 1, hi = ~0ull;    // invariant: count(u >= lo) >= k
+    unsigned long long theta = 0;
+    bool exact = false;                                 // count(u >= theta) == k: no tie handling needed
+    int slot = 0;
+    {
+        // tighten [lo, hi] to the frontier's own range first (two reductions instead of ~12 bisection steps)
+        unsigned long long mx = 0, mn = ~0ull;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int n = t == 0 ? n0 : stage(t);
+            int b, e;
+            chunk_of(n, b, e);
+            for (int i = b; i < e; ++i) {
+                const unsigned long long u = skeys[i];
+                if (u > ABSENT) { mx = max(mx, u); mn = min(mn, u); }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        unsigned long long* r64 = reinterpret_cast<unsigned long long*>(sh.scan_a);
+        __syncthreads();
+        if ((tid & 31) == 0) { r64[tid >> 5] = mx; r64[WARPS + (tid >> 5)] = mn; }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < WARPS; ++i) { mx = max(mx, r64[i]); mn = min(mn, r64[WARPS + i]); }
+        __syncthreads();
+        lo = mn; hi = mx;
+    }
+    if (k == frontier) { theta = lo; exact = true; }
+    while (!exact) {
+        if (lo == hi) { theta = lo; break; }
+        const unsigned long long mid = lo + ((hi - lo) >> 1) + 1;     // lo < mid <= hi
+        int c = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int n = n_tiles == 1 ? n0 : stage(t);
+            int b, e;
+            chunk_of(n, b, e);
+            for (int i = b; i < e; ++i) c += skeys[i] >= mid ? 1 : 0;
+        }
+        c = block_sum(c, sh.red, slot);
+        slot ^= 1;
+        if (c == k) { theta = mid; exact = true; break; }
+        if (c > k) lo = mid; else hi = mid - 1;
+    }
+    // ---- ordered compaction: keys > theta, then the lowest ids among keys == theta ----
+    int need_eq = 0;
+    if (!exact) {
+        int c = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int n = n_tiles == 1 ? n0 : stage(t);
+            int b, e;
+            chunk_of(n, b, e);
+            for (int i = b; i < e; ++i) c += skeys[i] > theta ? 1 : 0;
+        }
+        c = block_sum(c, sh.red, slot);
+        slot ^= 1;
+        need_eq = k - c;
+    }
+    int32_t* sel = a.exp_order + n_expanded;     // the wave's leaves, id order (doubles as the expansion record)
+    int run_sel = 0, run_eq = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int n = n_tiles == 1 ? n0 : stage(t);
+        const int base = t * STAGE_CAP;
+        int b, e;
+        chunk_of(n, b, e);
+        int cg = 0, ce = 0;
+        for (int i = b; i < e; ++i) {
+            const unsigned long long u = skeys[i];
+            if (exact) cg += u >= theta ? 1 : 0;
+            else { cg += u > theta ? 1 : 0; ce += u == theta ? 1 : 0; }
+        }
+        int eg, ee, tg, te;
+        block_scan2(cg, ce, sh, eg, ee, tg, te);
+        int eq_seen = run_eq + ee;
+        int pos = run_sel + eg + min(eq_seen, need_eq) - min(run_eq, need_eq);
+        for (int i = b; i < e; ++i) {
+            const unsigned long long u = skeys[i];
+            bool take;
+            if (exact) take = u >= theta;
+            else if (u > theta) take = true;
+            else if (u == theta) { take = eq_seen < need_eq; ++eq_seen; }
+            else take = false;
+            if (take) sel[pos++] = base + i;
+        }
+        run_sel += tg + min(run_eq + te, need_eq) - min(run_eq, need_eq);
+        run_eq += te;
+    }
+    __syncthreads();
+    // ---- children layout: ids by prefix sum of the available-action counts, in leaf-id order ----
+    int run = 0, term = 0;
+    for (int j0 = 0; j0 < k; j0 += THREADS) {
+        const int j = j0 + tid;
+        int leaf = 0, mask = 0, n = 0, meta = 0;
+        if (j < k) {
+            leaf = sel[j];
+            meta = __ldcg(a.tree.meta + leaf);
+            mask = a.cfg.env_kind == B2_ENV_HIGHWAY ? (meta >> 24) & 0x1f : (1 << a.cfg.n_actions) - 1;
+            n = __popc(mask);
+            term += (meta >> 16) & 1;
+        }
+        int en, e2, tn, t2;
+        block_scan2(n, 0, sh, en, e2, tn, t2);
+        if (j < k) {
+            const int c0 = n_nodes + run + en;
+            a.tree.first_child[leaf] = c0;
+            a.tree.meta[leaf] = meta | (n << 8);
+            a.keys[leaf] = -INFINITY;
+            int q = 0;
+            for (int act_i = 0; act_i < MAX_BRANCH; ++act_i) {
+                int act;
+                if (a.cfg.env_kind == B2_ENV_HIGHWAY) {
+                    if (act_i >= 5) break;
+                    const int order[5] = {hw::A_IDLE, hw::A_LEFT, hw::A_RIGHT, hw::A_FASTER, hw::A_SLOWER};
+                    act = order[act_i];
+                } else {
+                    if (act_i >= a.cfg.n_actions) break;
+                    act = act_i;
+                }
+                if (mask & (1 << act)) {
+                    a.work[run + en + q] = leaf | (act << 28);
+                    ++q;
+                }
+            }
+        }
+        run += tn;
+    }
+    term = block_sum(term, sh.red, slot);
+    if (tid == 0) {
+        Control* c = a.ctl;
+        c->term_exp += term;
+        a.wave_start[c->n_waves] = n_expanded;
+        c->n_waves += 1;
+        a.wave_start[c->n_waves] = n_expanded + k;
+        c->wave_base = n_nodes;
+        c->wave_children = run;
+        c->n_nodes = n_nodes + run;
+        c->n_expanded = n_expanded + k;
+    }
+    return run;
+}
+
+// node record of a new child: DeterministicNode.__init__ / update (deterministic.py:10-19, 45-63)
+__device__ __forceinline__ void write_child(const Args& a, int c, int leaf, int action, double r, bool done, int avail) {
+    const b2_opd_tree& tr = a.tree;
+    const int d = ld_cg(tr.depth + leaf) + 1;
+    double lo = ld_cg(tr.lower + leaf) + a.cfg.gamma_pow[d - 1] * r;
+    double up = lo + a.cfg.gamma_pow_div[d];
+    if (done) {
+        lo = lo + a.cfg.terminal_bonus[d];
+        up = lo;
+    }
+    tr.parent[c] = leaf;
+    tr.first_child[c] = -1;
+    tr.depth[c] = d;
+    tr.count[c] = 2;
+    tr.meta[c] = action | (done ? 1 << 16 : 0) | (avail << 24);
+    tr.reward[c] = r;
+    tr.lower[c] = lo;
+    tr.upper[c] = up;
+    a.keys[c] = up;
+    if (!(r >= 0.0 && r <= 1.0)) a.ctl->error = 1;     // :46-47
+    atomicMax(&a.ctl->max_depth, d);
+}
+
+__device__ __forceinline__ void load_state_cg(const int32_t* w, int li, hw::Lane& L, int& t, int& si) {
+    L.x = __int_as_float(__ldcg(w + 0 * hw::V + li));
+    L.y = __int_as_float(__ldcg(w + 1 * hw::V + li));
+    L.h = __int_as_float(__ldcg(w + 2 * hw::V + li));
+    L.v = __int_as_float(__ldcg(w + 3 * hw::V + li));
+    L.ts = __int_as_float(__ldcg(w + 4 * hw::V + li));
+    L.timer = __int_as_float(__ldcg(w + 5 * hw::V + li));
+    L.tgt = __ldcg(w + 6 * hw::V + li);
+    L.flags = __ldcg(w + 7 * hw::V + li);
+    t = __ldcg(w + 8 * hw::V + 0);
+    si = __ldcg(w + 8 * hw::V + 1);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
+    extern __shared__ unsigned long long skeys[];
+    __shared__ SelShared sh;
+    __shared__ float hw_scratch[GROUPS][hw::SCRATCH_FLOATS];
+    __shared__ int s_children, s_nodes, s_expanded;
+    const int tid = threadIdx.x, lane = tid & 31, li = tid & 15;
+    const unsigned n_ctas = gridDim.x;
+    Control* ctl = a.ctl;
+    const b2_opd_tree& tr = a.tree;
+    const bool hwy = a.cfg.env_kind == B2_ENV_HIGHWAY;
+    if (blockIdx.x == 0) {
+        // root: DeterministicNode.__init__ (:10-19)
+        int avail = 0;
+        if (hwy) {
+            for (int i = tid; i < hw::WORDS; i += THREADS) tr.state[i] = a.root_state[i];
+            avail = hw::avail_mask(__int_as_float(a.root_state[hw::V]), a.root_state[8 * hw::V + 1]);
+        } else if (tid == 0) {
+            tr.state[0] = a.root_state[0];
+        }
+        if (tid == 0) {
+            tr.parent[0] = -1; tr.first_child[0] = -1; tr.depth[0] = 0; tr.count[0] = 1;
+            tr.meta[0] = 0xff | (avail << 24);
+            tr.reward[0] = 0.0; tr.lower[0] = 0.0; tr.upper[0] = 0.0;
+            a.keys[0] = 0.0;
+            s_nodes = 1; s_expanded = 0;
+        }
+        __syncthreads();
+    }
+    // ------------------------------------------------------------------ waves
+    while (true) {
+        if (blockIdx.x == 0) {
+            const int nn = s_nodes, ne = s_expanded;
+            __syncthreads();
+            const int children = select_wave(a, sh, skeys, nn, ne);
+            if (tid == 0) {
+                s_children = children;
+                if (children == 0) ctl->stop = 1;
+                else { s_nodes = ctl->n_nodes; s_expanded = ctl->n_expanded; }
+            }
+        }
+        grid_barrier(ctl, n_ctas);
+        if (*(volatile int*)&ctl->stop) break;
+        const int total = *(volatile int*)&ctl->wave_children;
+        const int base = *(volatile int*)&ctl->wave_base;
+        if (hwy) {
+            // consecutive children go to different SMs first: a small wave runs one warp per SM
+            const int warp_global = (tid >> 5) * (int)n_ctas + (int)blockIdx.x;
+            const int n_warps = WARPS * (int)n_ctas;
+            for (int w0 = 2 * warp_global; w0 < total; w0 += 2 * n_warps) {
+                const int w = w0 + ((tid >> 4) & 1);
+                const bool real = w < total;
+                const int item = __ldcg(a.work + (real ? w : w0));
+                const int leaf = item & 0x0fffffff, action = real ? (item >> 28) & 7 : hw::A_IDLE;
+                hw::Lane L;
+                int t, si;
+                load_state_cg(tr.state + (int64_t)leaf * hw::WORDS, li, L, t, si);
+                bool term, trunc;
+                const float r = hw::step(L, li, t, si, action, term, trunc, 0xffffffffu, hw_scratch[tid >> 4]);
+                const float ego_y = __shfl_sync(0xffffffffu, L.y, 0, 16);
+                if (real) {
+                    const int c = base + w;
+                    hw::store_state(tr.state + (int64_t)c * hw::WORDS, li, L, t, si);
+                    if (li == 0) write_child(a, c, leaf, action, (double)r, term, hw::avail_mask(ego_y, si));
+                }
+            }
+        } else {
+            const b2_finite_mdp& m = a.cfg.mdp;
+            for (int w = blockIdx.x * THREADS + tid; w < total; w += THREADS * (int)n_ctas) {
+                const int item = __ldcg(a.work + w);
+                const int leaf = item & 0x0fffffff, action = (item >> 28) & 7;
+                const int s = ld_cg(tr.state + leaf);
+                const int s2 = m.transition[(int64_t)s * m.n_actions + action];
+                const int c = base + w;
+                tr.state[c] = s2;
+                write_child(a, c, leaf, action, m.reward[(int64_t)s * m.n_actions + action], m.terminal[s] != 0, 0);
+            }
+        }
+        grid_barrier(ctl, n_ctas);
+        if (*(volatile int*)&ctl->error) break;
+    }
+    if (blockIdx.x != 0) return;
+    // ------------------------------------------------------------------ bottom-up pass, reverse wave order
+    const volatile Control* vc = ctl;
+    const int n_waves = vc->n_waves, n_exp = vc->n_expanded, n_nodes = vc->n_nodes;
+    for (int w = n_waves - 1; w >= 0; --w) {
+        const int b = a.wave_start[w], e = a.wave_start[w + 1];
+        for (int j = b + tid; j < e; j += THREADS) {
+            const int p = a.exp_order[j];
+            const int fc = tr.first_child[p];
+            const int n = (tr.meta[p] >> 8) & 0xff;
+            double lo = -INFINITY, up = -INFINITY;
+            int desc = 0;
+            for (int q = 0; q < n; ++q) {
+                const double l2 = ld_cg(tr.lower + fc + q), u2 = ld_cg(tr.upper + fc + q);
+                lo = l2 > lo ? l2 : lo;
+                up = u2 > up ? u2 : up;
+                desc += ld_cg(tr.count + fc + q) - 1;
+            }
+            tr.lower[p] = lo;                       // backup_to_root (:74-79)
+            tr.upper[p] = up;
+            tr.count[p] = (p == 0 ? 1 : 2) + desc;  // :64-65
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (tid >= 32) return;
+    // get_plan (abstract.py:143-156) on value_lower; a tie is broken on the host with the planner RNG
+    int node = 0, len = 0, tie_node = -1;
+    while (true) {
+        const int fc = ld_cg(tr.first_child + node);
+        if (fc < 0) break;
+        const int n = (ld_cg(tr.meta + node) >> 8) & 0xff;
+        const double lo = lane < n ? ld_cg(tr.lower + fc + lane) : -INFINITY;
+        const double m = warp_max_f64(lo);
+        const unsigned eq = __ballot_sync(0xffffffffu, lane < n && lo == m);
+        if (__popc(eq) > 1) { tie_node = node; break; }
+        const int c = fc + __ffs(eq) - 1;
+        if (lane == 0 && len < a.cfg.plan_capacity) a.plan[len] = (int8_t)(ld_cg(tr.meta + c) & 0xff);
+        ++len;
+        node = c;
+    }
+    if (lane == 0) {
+        int32_t* res = a.result;
+        res[0] = n_nodes;
+        res[1] = n_nodes - n_exp;
+        res[2] = vc->max_depth;
+        res[3] = vc->term_exp;
+        res[4] = vc->error;
+        res[5] = len;
+        res[6] = tie_node;
+        res[7] = n_waves;
+    }
+}
+
+static int64_t align_up(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+struct Layout {
+    int64_t ctl, keys, exp_order, wave_start, work, total;
+};
+
+static Layout make_layout(const b2_opd_wave_config* c) {
+    Layout l;
+    l.ctl = 0;
+    l.keys = align_up(sizeof(Control));
+    l.exp_order = l.keys + align_up((int64_t)c->node_capacity * 8);
+    l.wave_start = l.exp_order + align_up((int64_t)c->n_expansions * 4 + 4);
+    l.work = l.wave_start + align_up(((int64_t)c->n_expansions + 2) * 4);
+    l.total = l.work + align_up((int64_t)c->width * c->n_actions * 4 + 4);
+    return l;
+}
+
+}  // namespace wave
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int64_t b2_opd_wave_workspace_bytes(const b2_opd_wave_config* cfg) {
+    if (!cfg || cfg->n_expansions < 0 || cfg->width <= 0 || cfg->n_actions <= 0) return -1;
+    return wave::make_layout(cfg).total;
+}
+
+extern "C" int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* root_state, const b2_opd_tree* tree,
+                                void* workspace, int8_t* plan, int32_t* result, void* stream_) {
+    B2_REQUIRE(cfg && root_state && tree && workspace && plan && result, "null pointer");
+    B2_REQUIRE(cfg->n_expansions >= 0 && cfg->width > 0, "bad budget / wave width");
+    B2_REQUIRE(cfg->n_actions > 0 && cfg->n_actions <= wave::MAX_BRANCH, "n_actions must be in 1..8");
+    B2_REQUIRE((int64_t)cfg->node_capacity >= 1 + (int64_t)cfg->n_expansions * cfg->n_actions, "node_capacity too small");
+    B2_REQUIRE(cfg->node_capacity < (1 << 28), "node_capacity must be < 2^28");
+    B2_REQUIRE(cfg->plan_capacity >= 1, "plan_capacity too small");
+    B2_REQUIRE(cfg->gamma_pow && cfg->gamma_pow_div && cfg->terminal_bonus, "gamma tables missing");
+    if (cfg->env_kind == B2_ENV_FINITE) {
+        B2_REQUIRE(cfg->mdp.transition && cfg->mdp.reward && cfg->mdp.terminal, "finite MDP tables missing");
+        B2_REQUIRE(cfg->mdp.n_actions == cfg->n_actions, "mdp.n_actions != n_actions");
+    } else if (cfg->env_kind == B2_ENV_HIGHWAY) {
+        B2_REQUIRE(cfg->n_actions == B2_HW_ACTIONS, "HighwayLite has 5 actions");
+    } else {
+        set_error("unknown env_kind %d", cfg->env_kind);
+        return B2_ERR_INVALID;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const wave::Layout l = wave::make_layout(cfg);
+    char* ws = (char*)workspace;
+    wave::Args a;
+    a.cfg = *cfg; a.tree = *tree; a.root_state = root_state;
+    a.ctl = (wave::Control*)(ws + l.ctl);
+    a.keys = (double*)(ws + l.keys);
+    a.exp_order = (int32_t*)(ws + l.exp_order);
+    a.wave_start = (int32_t*)(ws + l.wave_start);
+    a.work = (int32_t*)(ws + l.work);
+    a.plan = plan; a.result = result;
+    B2_CUDA_CHECK(cudaMemsetAsync(a.ctl, 0, sizeof(wave::Control), stream));
+    const int stage = cfg->node_capacity < wave::STAGE_CAP ? cfg->node_capacity : wave::STAGE_CAP;
+    const size_t smem = (size_t)stage * 8;
+    B2_CUDA_CHECK(cudaFuncSetAttribute(wave::opd_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    B2_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave::opd_wave_kernel, wave::THREADS, smem));
+    B2_REQUIRE(per_sm >= 1, "wave kernel does not fit on an SM");
+    // one CTA per SM; a wave of w children keeps ceil(w / 16) CTAs busy, the others only pass the barriers
+    int grid = sm_count();
+    if (cfg->max_ctas > 0 && cfg->max_ctas < grid) grid = cfg->max_ctas;
+    void* params[] = {&a};
+    B2_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)wave::opd_wave_kernel, dim3(grid), dim3(wave::THREADS), params,
+                                              smem, stream));
+    return B2_OK;
+}

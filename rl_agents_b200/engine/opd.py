@@ -4,7 +4,7 @@ import logging
 import numpy as np
 
 from rl_agents_b200 import _lib
-from rl_agents_b200.engine.tables import FiniteTables, gamma_tables
+from rl_agents_b200.engine.tables import FiniteTables, gamma_tables, terminal_bonus_table
 
 logger = logging.getLogger(__name__)
 
@@ -30,6 +30,8 @@ class OPDEngine(object):
         gp, gd = gamma_tables(gamma, self.n_expansions + 2)
         self.gamma_pow = torch.as_tensor(gp, device=self.device)
         self.gamma_pow_div = torch.as_tensor(gd, device=self.device)
+        self.terminal_bonus = torch.as_tensor(terminal_bonus_table(terminal_reward, gamma, self.n_expansions + 2),
+                                              device=self.device)
         self.tables = FiniteTables(mdp, self.device) if env_kind == _lib.ENV_FINITE else None
         shape = (self.n_trees, self.capacity)
         i32, f64 = torch.int32, torch.float64
@@ -46,7 +48,8 @@ class OPDEngine(object):
         self.cfg = _lib.OPDConfig(env_kind, self.n_trees, self.n_actions, self.n_expansions, self.capacity,
                                   self.plan_capacity, 1 if keys_in_smem else 0, int(kernel), float(terminal_reward),
                                   self.gamma_pow.data_ptr(), self.gamma_pow_div.data_ptr(),
-                                  self.tables.struct() if self.tables else _lib.FiniteMDP())
+                                  self.tables.struct() if self.tables else _lib.FiniteMDP(),
+                                  self.terminal_bonus.data_ptr())
         self.tree = _lib.OPDTree(*[t.data_ptr() for t in (self.parent, self.first_child, self.depth, self.count,
                                                           self.meta, self.reward, self.lower, self.upper, self.state)])
         ws = self.lib.b2_opd_workspace_bytes(self.cfg)
@@ -105,3 +108,34 @@ class OPDEngine(object):
                 "first_child": self.first_child[tree, :n].cpu().numpy(), "n_children": (meta >> 8) & 0xff,
                 "done": ((meta >> 16) & 1).astype(bool), "reward": self.reward[tree, :n].cpu().numpy(),
                 "lower": self.lower[tree, :n].cpu().numpy(), "upper": self.upper[tree, :n].cpu().numpy()}
+
+
+class OPDWaveEngine(OPDEngine):
+    """ONE OPD decision searched by the whole GPU in waves of `width` leaves (b2_opd_plan_wave).
+
+    width = 1 is the reference's strict best-first order; any width is bit-identical with the specification
+    oracle/planners.py::opd_plan_wavefront.  Same tensors / finish() / tree_dict() as OPDEngine with
+    n_trees = 1."""
+
+    def __init__(self, env_kind, n_actions, budget, gamma, width, terminal_reward=0.0, mdp=None, device="cuda",
+                 max_ctas=0):
+        super(OPDWaveEngine, self).__init__(env_kind, 1, n_actions, budget, gamma, terminal_reward, mdp, device)
+        self.width = int(width)
+        self.wcfg = _lib.OPDWaveConfig(env_kind, self.n_actions, self.n_expansions, self.capacity, self.plan_capacity,
+                                       self.width, int(max_ctas), 0, self.gamma_pow.data_ptr(),
+                                       self.gamma_pow_div.data_ptr(), self.terminal_bonus.data_ptr(),
+                                       self.tables.struct() if self.tables else _lib.FiniteMDP())
+        ws = self.lib.b2_opd_wave_workspace_bytes(self.wcfg)
+        if ws < 0:
+            raise _lib.B2Error("unsupported wavefront OPD configuration")
+        self.workspace = self.torch.empty(int(ws), dtype=self.torch.uint8, device=self.device)
+
+    def plan(self, root_state):
+        """root_state: int32 device tensor [1] (finite) or [136] / [1, 136]."""
+        assert root_state.dtype == self.torch.int32 and root_state.is_cuda and root_state.is_contiguous()
+        _lib.check(self.lib.b2_opd_plan_wave(self.wcfg, _lib.ptr(root_state), self.tree, _lib.ptr(self.workspace),
+                                             _lib.ptr(self.plan_buf), _lib.ptr(self.result), _lib.current_stream()))
+
+    @property
+    def n_waves(self):
+        return int(self.result[0, 7].item())

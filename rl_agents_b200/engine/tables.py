@@ -12,6 +12,14 @@ def gamma_tables(gamma, n):
     return gp, gd
 
 
+def terminal_bonus_table(terminal_reward, gamma, n):
+    """(terminal_reward * gamma**d) / (1 - gamma), the reference's association (deterministic.py:60-63)."""
+    gamma, tr = float(gamma), float(terminal_reward)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.array([(tr * gamma ** d) / (1 - gamma) if gamma != 1 else np.inf * tr for d in range(n)],
+                        dtype=np.float64)
+
+
 def uniform_cdf_table(n_actions):
     """Row n: cumsum(ones(n)/n)/cumsum[-1] -- the cdf Generator.choice(a, 1, p=p)
     searches for a uniform p over n actions (mcts.py:60-72,172)."""

@@ -70,4 +70,6 @@ class FiniteMDPEnv(object):
             k = int(self.np_random.choice(p.size, p=p))
             s2 = k if m.mode == "stochastic" else int(m.next[s, action, k])
         m.state = s2
-        return s2, r, bool(m.terminal[s2]), False, {}
+        # the `finite_mdp` package's MDP.step evaluates done on the state the action was taken IN
+        # (consistent with value_iteration.py:62, which zeroes the next-value of terminal SOURCE states)
+        return s2, r, bool(m.terminal[s]), False, {}

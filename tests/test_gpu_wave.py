@@ -1,0 +1,158 @@
+"""GPU parity tests of the wavefront OPD (b2_opd_plan_wave): bit-exact against its specification
+(oracle/planners.py::opd_plan_wavefront and the same statement in C), width 1 against the reference's
+strict algorithm (oracle.planners.opd_plan, pinned to the reference's golden trees)."""
+import numpy as np
+import pytest
+
+from oracle import envs as oenvs
+from oracle import planners
+from tests.util import load_mdps
+
+pytestmark = pytest.mark.gpu
+M = load_mdps()
+
+
+def np_random(seed):
+    return np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+
+
+def finite(name="large1", terminal=None):
+    from rl_agents_b200.envs.finite_mdp import FiniteMDP
+    term = M[name + "_term"] if terminal is None else terminal
+    return FiniteMDP("deterministic", M[name + "_T"], M[name + "_R"], term), \
+        lambda: oenvs.FiniteMDPLite(M[name + "_T"], M[name + "_R"], term)
+
+
+def check(eng, plan, tree):
+    plans, res = eng.finish([np_random(0)])
+    d = eng.tree_dict(0)
+    assert d["parent"].tolist() == list(tree.parent)
+    assert d["action"].tolist() == list(tree.action)
+    assert d["depth"].tolist() == list(tree.depth)
+    assert d["count"].tolist() == list(tree.count)
+    assert d["first_child"].tolist() == list(tree.first_child)
+    assert d["n_children"].tolist() == list(tree.n_children)
+    assert d["done"].tolist() == [bool(x) for x in tree.done]
+    assert np.array_equal(d["reward"], np.array(tree.reward))
+    assert np.array_equal(d["lower"], np.array(tree.lower))
+    assert np.array_equal(d["upper"], np.array(tree.upper))
+    assert plans[0] == plan
+    assert int(res[0, 1]) == tree.n_leaves
+    return res
+
+
+@pytest.mark.parametrize("width", [1, 2, 5, 16, 64, 300, 5000])
+def test_wave_finite_matches_the_specification(width):
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    mdp, make = finite()
+    eng = OPDWaveEngine(_lib.ENV_FINITE, 5, 500, 0.9, width, mdp=mdp)
+    eng.plan(torch.tensor([0], dtype=torch.int32, device="cuda"))
+    plan, tree = planners.opd_plan_wavefront(make(), 500, 0.9, width, np_random=np_random(0))
+    res = check(eng, plan, tree)
+    assert int(res[0, 7]) == len(tree.waves)
+    if width == 1:      # the reference's own algorithm
+        plan1, t1 = planners.opd_plan(make(), 500, 0.9, np_random=np_random(0))
+        assert plan1 == plan and t1.parent == tree.parent and t1.count == tree.count and t1.upper == tree.upper
+
+
+def test_wave_finite_terminal_states_and_terminal_reward():
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    term = M["large1_term"].copy()
+    term[[3, 17, 66, 91]] = True
+    mdp, make = finite(terminal=term)
+    for width, tr in ((1, 0.3), (8, 0.3), (32, -0.7), (8, 0.1)):
+        eng = OPDWaveEngine(_lib.ENV_FINITE, 5, 400, 0.8, width, terminal_reward=tr, mdp=mdp)
+        eng.plan(torch.tensor([0], dtype=torch.int32, device="cuda"))
+        plan, tree = planners.opd_plan_wavefront(make(), 400, 0.8, width, terminal_reward=tr, np_random=np_random(0))
+        res = check(eng, plan, tree)
+        assert int(res[0, 3]) == tree.terminal_expansions
+
+
+def test_wave_finite_many_exact_ties():
+    """All rewards equal: every frontier key of a depth ties; the wave must take the lowest node ids."""
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    from rl_agents_b200.envs.finite_mdp import FiniteMDP
+    rng = np.random.default_rng(3)
+    T = rng.integers(0, 30, size=(30, 4)).astype(np.int32)
+    R = np.full((30, 4), 0.5)
+    R[:, 2] = 1.0               # reward 1: children tie with their parent's key as well
+    term = np.zeros(30, bool)
+    for width in (1, 3, 7, 50):
+        eng = OPDWaveEngine(_lib.ENV_FINITE, 4, 600, 0.8, width, mdp=FiniteMDP("deterministic", T, R, term))
+        eng.plan(torch.tensor([0], dtype=torch.int32, device="cuda"))
+        plan, tree = planners.opd_plan_wavefront(oenvs.FiniteMDPLite(T, R, term), 600, 0.8, width, np_random=np_random(0))
+        check(eng, plan, tree)
+
+
+def test_wave_finite_reward_out_of_range_raises():
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    from rl_agents_b200.envs.finite_mdp import FiniteMDP
+    R = M["large1_R"].copy()
+    R[5, 2] = 1.5
+    eng = OPDWaveEngine(_lib.ENV_FINITE, 5, 2000, 0.9, 16, mdp=FiniteMDP("deterministic", M["large1_T"], R, M["large1_term"]))
+    eng.plan(torch.tensor([0], dtype=torch.int32, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.finish([np_random(0)])
+
+
+@pytest.mark.parametrize("width,seed", [(1, 0), (4, 1), (32, 2), (32, 7)])
+def test_wave_highway_matches_the_specification(width, seed):
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    words = oenvs.make_highway_state(seed).pack()
+    eng = OPDWaveEngine(_lib.ENV_HIGHWAY, 5, 400, 0.8, width)
+    eng.plan(torch.tensor(words, dtype=torch.int32, device="cuda"))
+    plan, tree = planners.opd_plan_wavefront(oenvs.HighwayLite(seed=seed), 400, 0.8, width, np_random=np_random(0))
+    check(eng, plan, tree)
+
+
+def c_check(eng, c):
+    plans, res = eng.finish([np_random(0)])
+    d = eng.tree_dict(0)
+    for k in ("parent", "action", "depth", "count", "first_child", "n_children", "reward", "lower", "upper"):
+        assert np.array_equal(d[k], c[k]), k
+    assert np.array_equal(d["done"], c["done"].astype(bool))
+    assert int(res[0, 1]) == c["n_leaves"]
+    return res
+
+
+@pytest.mark.parametrize("width", [1, 64, 128])
+def test_wave_highway_c2_full_size_vs_c_specification(width):
+    """BASELINE C2 (budget 10 000, gamma 0.8) as ONE decision."""
+    import torch
+    from oracle import c_oracle
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    eng = OPDWaveEngine(_lib.ENV_HIGHWAY, 5, 10000, 0.8, width)
+    for seed in (0, 5):
+        words = oenvs.make_highway_state(seed).pack()
+        eng.plan(torch.tensor(words, dtype=torch.int32, device="cuda"))
+        c = c_oracle.opd_plan_wave(words, 10000, 0.8, width)
+        res = c_check(eng, c)
+        assert int(res[0, 7]) == c["n_waves"]
+        if width == 1:
+            s = c_oracle.opd_plan(words, 10000, 0.8)
+            assert np.array_equal(s["parent"], c["parent"]) and np.array_equal(s["upper"], c["upper"])
+
+
+def test_wave_highway_large_budget_multi_tile_vs_c_specification():
+    """200 000 child nodes: the frontier no longer fits one shared-memory tile."""
+    import torch
+    from oracle import c_oracle
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    eng = OPDWaveEngine(_lib.ENV_HIGHWAY, 5, 200000, 0.8, 1024)
+    words = oenvs.make_highway_state(2).pack()
+    eng.plan(torch.tensor(words, dtype=torch.int32, device="cuda"))
+    c = c_oracle.opd_plan_wave(words, 200000, 0.8, 1024)
+    res = c_check(eng, c)
+    assert int(res[0, 7]) == c["n_waves"]

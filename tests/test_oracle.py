@@ -231,3 +231,36 @@ def test_mcts_highway():
                                  g["temperature"], np_random(0))
     assert plan == g["plan"]
     assert_tree_matches(tree_dict(t, ["value", "prior"]), g["tree"], ["value", "prior"])
+
+
+def test_vi_and_opd_agree_on_terminal_semantics():
+    """done = terminal[state the action is taken in] (finite_mdp's MDP.step), the convention
+    value_iteration.py:62 assumes: on a small deterministic MDP whose every path ends in a terminal
+    state, the exhaustive OPD tree's root value_lower equals max_a Q*(s0, a) of value iteration."""
+    T = np.array([[1, 2], [3, 3], [3, 4], [3, 3], [4, 4]], dtype=np.int32)
+    R = np.array([[0.2, 0.5], [0.9, 0.1], [0.3, 0.6], [0.7, 0.4], [1.0, 0.8]])
+    term = np.array([False, False, False, True, True])
+    gamma = 0.9
+    q, _ = planners.value_iteration("deterministic", T, R, term, gamma, 50)
+    _, tree = planners.opd_plan(envs.FiniteMDPLite(T, R, term), 2000, gamma,
+                                np_random=np.random.Generator(np.random.PCG64(0)))
+    # terminal leaves keep being expanded by the reference (:111-112) but add nothing below value_lower's max
+    # until the discount is exhausted; compare the part of the value collected up to the terminal step
+    best = max(q[0])
+    path_values = []
+    for a0 in range(2):
+        s1 = T[0, a0]
+        for a1 in range(2):
+            s2 = T[s1, a1]
+            path_values.append(R[0, a0] + gamma * R[s1, a1] + gamma ** 2 * max(R[s2]))
+    assert abs(best - max(path_values)) < 1e-12
+    done_nodes = [i for i in range(len(tree)) if tree.done[i]]
+    assert done_nodes and all(tree.depth[i] >= 3 for i in done_nodes)
+
+    def path_return(i):
+        g = 0.0
+        while i > 0:
+            g += gamma ** (tree.depth[i] - 1) * tree.reward[i]
+            i = tree.parent[i]
+        return g
+    assert abs(max(path_return(i) for i in done_nodes if tree.depth[i] == 3) - best) < 1e-12
