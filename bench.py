@@ -509,6 +509,11 @@ def run_b200(a):
                      "note": "latency/FP32-issue bound by construction (15 dependent sub-steps per child); "
                              "HBM fraction reported as the contract asks, see DESIGN.md section 4"},
     }
+    if rank == 0:
+        try:
+            out["single_decision"] = single_decision_latency(a, dev)
+        except Exception as e:          # an auxiliary measurement must never take the headline down
+            out["single_decision"] = {"error": str(e)[:300]}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(a.budget, a.gamma, a.cpu_box)
         try:
@@ -519,6 +524,73 @@ def run_b200(a):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def single_decision_latency(a, dev, reps=5):
+    """ONE C2 decision (what agent.plan() does under scripts/experiments.py) at a time: the strict one-CTA
+    kernel and the wavefront kernel (b2_opd_plan_wave) at a few widths, plus one budget-1e6 decision.
+    CUDA-event median over `reps` launches per scene; quality of each width against the strict tree
+    (root action agreement, gap of the root value_lower) on the same scenes."""
+    import numpy as np
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDEngine, OPDWaveEngine
+    from rl_agents_b200.envs.highway_lite import make_scene
+    scenes = [torch.tensor(make_scene(s), dtype=torch.int32, device=dev) for s in range(4)]
+    n_exp = a.budget // N_ACTIONS
+
+    def med_ms(fn):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    rows = []
+    eng = OPDEngine(_lib.ENV_HIGHWAY, 1, N_ACTIONS, a.budget, a.gamma, keys_in_smem=True, device=dev)
+    ms = float(np.median([med_ms(lambda: eng.plan(s.reshape(1, -1))) for s in scenes]))
+    strict = []
+    for s in scenes:
+        eng.plan(s.reshape(1, -1))
+        plans, _ = eng.finish([np.random.default_rng(0)])
+        strict.append((plans[0][0], float(eng.lower[0, 0].item())))
+    rows.append({"mode": "strict (reference order, one CTA)", "ms": ms, "expansions_per_s": n_exp / (ms * 1e-3)})
+    del eng
+    for width in (16, 64, 128):
+        eng = OPDWaveEngine(_lib.ENV_HIGHWAY, N_ACTIONS, a.budget, a.gamma, width, device=dev)
+        ms = float(np.median([med_ms(lambda: eng.plan(s)) for s in scenes]))
+        agree, gaps, waves = 0, [], []
+        for s, (act, low) in zip(scenes, strict):
+            eng.plan(s)
+            plans, res = eng.finish([np.random.default_rng(0)])
+            agree += int(plans[0][0] == act)
+            gaps.append(low - float(eng.lower[0, 0].item()))
+            waves.append(int(res[0, 7]))
+        rows.append({"mode": "wavefront", "width": width, "ms": ms, "expansions_per_s": n_exp / (ms * 1e-3),
+                     "waves": float(np.mean(waves)), "root_action_agreement_vs_strict": agree / float(len(scenes)),
+                     "root_value_lower_gap_vs_strict_max": float(max(gaps)),
+                     "root_value_lower_strict_mean": float(np.mean([l for _, l in strict]))})
+        del eng
+    big = {}
+    try:
+        eng = OPDWaveEngine(_lib.ENV_HIGHWAY, N_ACTIONS, 1000000, a.gamma, 1024, device=dev)
+        ms = med_ms(lambda: eng.plan(scenes[0]))
+        eng.plan(scenes[0])
+        _, res = eng.finish([np.random.default_rng(0)])
+        big = {"budget": 1000000, "expansions": 200000, "width": 1024, "ms": float(ms), "waves": int(res[0, 7]),
+               "expansions_per_s": 200000 / (ms * 1e-3), "max_depth": int(res[0, 2])}
+        del eng
+    except Exception as e:
+        big = {"error": str(e)[:200]}
+    return {"workload": "ONE C2 decision: OPD on HighwayLite, budget %d, gamma %g" % (a.budget, a.gamma),
+            "specification": "oracle/planners.py::opd_plan_wavefront (bit-exact, tests/test_gpu_wave.py); width 1 = reference",
+            "rows": rows, "budget_1e6_decision": big}
 
 
 def main():

@@ -67,6 +67,10 @@ def main():
             if a.strict:
                 agree += int(plans[0][0] == strict_action[i])
                 gaps.append(strict_lower[i] - float(eng.lower[0, 0].item()))
+        names = ["stage", "bisect", "compact_layout", "barrier_after_select", "simulate", "barrier_after_simulate", "finish"]
+        prof = res[0, 8:16].astype(float)
+        row["prof_us_per_wave"] = {n: round(float(prof[i]) * 256 / 1965.0 / waves[-1], 2) for i, n in enumerate(names)}
+        row["bisection_steps_per_wave"] = float(prof[7]) / waves[-1]
         row["waves"] = float(np.mean(waves))
         row["us_per_wave"] = 1e3 * float(ms) / row["waves"]
         if a.strict:

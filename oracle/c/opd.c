@@ -102,7 +102,7 @@ static int cmp_int(const void* a, const void* b) { return *(const int32_t*)a - *
 /* SPECIFICATION of the wavefront OPD (oracle/planners.py::opd_plan_wavefront, same statement in C): per wave
  * the k = min(width, expansions left, frontier size) best leaves by (upper desc, id asc) are expanded in
  * increasing id order; counts and backups bottom-up afterwards.  width = 1 is opd_highway_plan. */
-int opd_highway_plan_wave(const int32_t* root_words, int budget, double gamma, double terminal_reward, int width,
+int opd_highway_plan_wave(const int32_t* root_words, int budget, double gamma, double terminal_reward, int width, int lag,
                           int32_t* parent, int32_t* action, int32_t* depth, int32_t* count, int32_t* first_child,
                           int32_t* n_children, int32_t* done, double* reward, double* lower, double* upper,
                           int32_t* n_leaves, int32_t* n_waves) {
@@ -111,15 +111,25 @@ int opd_highway_plan_wave(const int32_t* root_words, int budget, double gamma, d
     hl_state* states = (hl_state*)malloc((size_t)cap * sizeof(hl_state));
     int32_t* heap = (int32_t*)malloc((size_t)cap * sizeof(int32_t));
     int32_t* chosen = (int32_t*)malloc((size_t)(width > 0 ? width : 1) * sizeof(int32_t));
+    /* lag = 1 (pipelined waves): the children of a wave become eligible one wave later -- wave w is chosen
+     * from the frontier as it was before wave w-1's children were added (unless nothing else is left) */
+    int32_t* pending = (int32_t*)malloc((size_t)cap * sizeof(int32_t));
+    int n_pending = 0;
     int heap_n = 0, n = 1, remaining = n_exp, waves = 0;
     memcpy(&states[0], root_words, sizeof(hl_state));
     parent[0] = -1; action[0] = -1; depth[0] = 0; count[0] = 1; first_child[0] = -1; n_children[0] = 0; done[0] = 0;
     reward[0] = lower[0] = upper[0] = 0.0;
     heap_push(&t, heap, &heap_n, 0);
     while (remaining > 0) {
+        if (heap_n == 0) {                       /* only the held-back children are left: release them */
+            for (int j = 0; j < n_pending; ++j) heap_push(&t, heap, &heap_n, pending[j]);
+            n_pending = 0;
+        }
         int k = width < remaining ? width : remaining;
         if (k > heap_n) k = heap_n;
         for (int j = 0; j < k; ++j) chosen[j] = heap_pop(&t, heap, &heap_n);
+        for (int j = 0; j < n_pending; ++j) heap_push(&t, heap, &heap_n, pending[j]);
+        n_pending = 0;
         qsort(chosen, (size_t)k, sizeof(int32_t), cmp_int);
         for (int j = 0; j < k; ++j) {
             const int leaf = chosen[j];
@@ -133,14 +143,14 @@ int opd_highway_plan_wave(const int32_t* root_words, int budget, double gamma, d
                 states[c] = states[leaf];
                 int flags;
                 const double r = (double)hl_step(&states[c], acts[q], &flags);
-                if (!(r >= 0.0 && r <= 1.0)) { free(states); free(heap); free(chosen); return -1; }
+                if (!(r >= 0.0 && r <= 1.0)) { free(states); free(heap); free(chosen); free(pending); return -1; }
                 parent[c] = leaf; action[c] = acts[q]; depth[c] = d; count[c] = 1; first_child[c] = -1; n_children[c] = 0;
                 done[c] = flags & 1;
                 reward[c] = r;
                 lower[c] = lower[leaf] + pow(gamma, d - 1) * r;
                 upper[c] = lower[c] + pow(gamma, d) / (1 - gamma);
                 if (done[c]) { lower[c] = lower[c] + terminal_reward * pow(gamma, d) / (1 - gamma); upper[c] = lower[c]; }
-                heap_push(&t, heap, &heap_n, c);
+                if (lag) pending[n_pending++] = c; else heap_push(&t, heap, &heap_n, c);
             }
         }
         remaining -= k;
@@ -159,11 +169,12 @@ int opd_highway_plan_wave(const int32_t* root_words, int budget, double gamma, d
         lower[p] = lo;
         upper[p] = up;
     }
-    *n_leaves = heap_n;
+    *n_leaves = heap_n + n_pending;
     *n_waves = waves;
     free(states);
     free(heap);
     free(chosen);
+    free(pending);
     return n;
 }
 

@@ -65,7 +65,7 @@ def opd_plan(root_words, budget, gamma, terminal_reward=0.0):
     return out
 
 
-def opd_plan_wave(root_words, budget, gamma, width, terminal_reward=0.0):
+def opd_plan_wave(root_words, budget, gamma, width, terminal_reward=0.0, lag=0):
     """The wavefront specification (oracle.planners.opd_plan_wavefront) in C; same dict as opd_plan + n_waves."""
     lib = load()
     cap = 1 + (int(budget) // 5) * 5
@@ -75,7 +75,7 @@ def opd_plan_wave(root_words, budget, gamma, width, terminal_reward=0.0):
     n_leaves, n_waves = ctypes.c_int32(0), ctypes.c_int32(0)
     root = np.ascontiguousarray(root_words, dtype=np.int32)
     n = lib.opd_highway_plan_wave(_p(root), ctypes.c_int(int(budget)), ctypes.c_double(gamma),
-                                  ctypes.c_double(terminal_reward), ctypes.c_int(int(width)),
+                                  ctypes.c_double(terminal_reward), ctypes.c_int(int(width)), ctypes.c_int(int(lag)),
                                   _p(i32["parent"]), _p(i32["action"]), _p(i32["depth"]), _p(i32["count"]),
                                   _p(i32["first_child"]), _p(i32["n_children"]), _p(i32["done"]), _p(f64["reward"]),
                                   _p(f64["lower"]), _p(f64["upper"]), ctypes.byref(n_leaves), ctypes.byref(n_waves))

@@ -4,7 +4,7 @@ import numpy as np
 
 from rl_agents_b200.agents.common.abstract import register_with_reference
 from rl_agents_b200.agents.tree_search.abstract import AbstractPlanner, AbstractTreeSearchAgent
-from rl_agents_b200.envs.adapters import describe
+from rl_agents_b200.envs.adapters import describe, mdp_fingerprint
 
 
 def horizon_for(episodes, gamma):
@@ -44,7 +44,7 @@ class MCTS(AbstractPlanner):
     def _engine_for(self, d, replicas, episodes):
         from rl_agents_b200.engine.mcts import MCTSEngine
         key = (d.kind, d.n_actions, replicas, episodes, self.config["horizon"], self.config["gamma"],
-               self.config["temperature"], id(d.mdp))
+               self.config["temperature"], mdp_fingerprint(d.mdp))
         if key != self._engine_key:
             # "subtree" keeps nodes alive for up to `horizon` decisions (a node at depth d survives d re-rootings)
             capacity = None

@@ -3,7 +3,7 @@ rl_agents.agents.tree_search.olop.OLOPAgent (olop.py:11-200)."""
 from rl_agents_b200.agents.common.abstract import register_with_reference
 from rl_agents_b200.agents.tree_search.abstract import AbstractPlanner, AbstractTreeSearchAgent
 from rl_agents_b200.agents.tree_search.mcts import allocation
-from rl_agents_b200.envs.adapters import describe
+from rl_agents_b200.envs.adapters import describe, mdp_fingerprint
 
 
 class OLOP(AbstractPlanner):
@@ -28,7 +28,7 @@ class OLOP(AbstractPlanner):
         from rl_agents_b200.engine.olop import OLOPEngine
         ub = self.config["upper_bound"]
         key = (d.kind, d.n_actions, self.config["episodes"], self.config["horizon"], self.config["gamma"],
-               ub["type"], ub["time"], ub["threshold"], self.config["continuation_type"], id(d.mdp))
+               ub["type"], ub["time"], ub["threshold"], self.config["continuation_type"], mdp_fingerprint(d.mdp))
         if key != self._engine_key:
             self.engine = OLOPEngine(d.kind, 1, d.n_actions, self.config["episodes"], self.config["horizon"],
                                      self.config["gamma"], ub, self.config["continuation_type"], mdp=d.mdp)

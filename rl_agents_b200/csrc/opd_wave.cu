@@ -25,7 +25,10 @@
 namespace b2 {
 namespace wave {
 
-constexpr int THREADS = 256;
+#ifndef B2_WAVE_THREADS
+#define B2_WAVE_THREADS 256
+#endif
+constexpr int THREADS = B2_WAVE_THREADS;
 constexpr int WARPS = THREADS / 32;
 constexpr int GROUPS = THREADS / 16;
 constexpr int STAGE_CAP = 24576;            // fp64 keys staged in shared memory per tile (192 KB)
@@ -35,6 +38,8 @@ struct Control {                            // head of the workspace; zeroed by 
     unsigned bar_count, bar_gen;
     int n_nodes, n_expanded, wave_children, wave_base, n_waves, stop;
     int error, max_depth, term_exp, pad;
+    long long prof[8];   // CTA 0 clock64 totals: 0 stage, 1 range+bisection, 2 compaction+layout, 3 barrier after select,
+                         // 4 simulate (CTA 0's share), 5 barrier after simulate, 6 bottom-up + plan, 7 bisection steps
 };
 
 struct Args {
@@ -90,7 +95,7 @@ __device__ __forceinline__ int block_sum(int v, int* red, int slot) {   // red: 
 }
 
 struct SelShared {
-    int red[4 * WARPS];
+    int red[4 * WARPS];        // two slots x two packed words
     int scan_a[THREADS], scan_b[THREADS];
     unsigned long long theta;
     int k, need_eq, total_children;
@@ -121,16 +126,22 @@ __device__ __forceinline__ void block_scan2(int a, int b, SelShared& sh, int& ea
 }
 
 // CTA 0: choose this wave's leaves and lay out their children.  Returns the number of children (0: done).
-__device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* skeys, int n_nodes, int n_expanded) {
+__device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* skeys, int n_nodes, int n_expanded,
+                           int staged_nodes, long long* prof) {
     const int tid = threadIdx.x;
+    long long t0 = clock64();
     const int remaining = a.cfg.n_expansions - n_expanded;
     const int frontier = n_nodes - n_expanded;
     const int k = min(min(a.cfg.width, remaining), frontier);
     if (k <= 0) return 0;
-    const int n_tiles = (n_nodes + STAGE_CAP - 1) / STAGE_CAP;
+    // a tree that fits one tile keeps its keys resident in shared memory: only the children of the previous
+    // wave (ids >= staged_nodes) are fetched; larger trees are streamed tile by tile on every pass
+    const bool resident = a.cfg.node_capacity <= STAGE_CAP;
+    const int n_tiles = resident ? 1 : (n_nodes + STAGE_CAP - 1) / STAGE_CAP;
     auto stage = [&](int tile) {
         const int base = tile * STAGE_CAP, n = min(STAGE_CAP, n_nodes - base);
         __syncthreads();
+#pragma unroll 8
         for (int i = tid; i < n; i += THREADS) skeys[i] = sortable(__ldcg(a.keys + base + i));
         __syncthreads();
         return n;
@@ -141,7 +152,15 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
         lo = min(tid * c, n);
         hi = min(lo + c, n);
     };
-    int n0 = stage(0);
+    int n0;
+    if (resident) {
+        for (int i = staged_nodes + tid; i < n_nodes; i += THREADS) skeys[i] = sortable(__ldcg(a.keys + i));
+        __syncthreads();
+        n0 = n_nodes;
+    } else {
+        n0 = stage(0);
+    }
+    if (tid == 0) { const long long t1 = clock64(); prof[0] += t1 - t0; t0 = t1; }
     // ---- bisection on the 64-bit images: largest theta with count(u >= theta) >= k ----
     unsigned long long lo = ABSENT + 1, hi = ~0ull;    // invariant: count(u >= lo) >= k
     unsigned long long theta = 0;
@@ -154,6 +173,7 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
             const int n = t == 0 ? n0 : stage(t);
             int b, e;
             chunk_of(n, b, e);
+#pragma unroll 8
             for (int i = b; i < e; ++i) {
                 const unsigned long long u = skeys[i];
                 if (u > ABSENT) { mx = max(mx, u); mn = min(mn, u); }
@@ -174,21 +194,51 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
         lo = mn; hi = mx;
     }
     if (k == frontier) { theta = lo; exact = true; }
+    int steps = 0;
     while (!exact) {
+        ++steps;
         if (lo == hi) { theta = lo; break; }
-        const unsigned long long mid = lo + ((hi - lo) >> 1) + 1;     // lo < mid <= hi
-        int c = 0;
+        // five-way split: four thresholds lo < m1 <= m2 <= m3 <= m4 <= hi per pass over the keys
+        const unsigned long long range = hi - lo, fifth = range / 5;
+        unsigned long long m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = range >= 5 ? lo + fifth * (j + 1) : min(lo + (unsigned long long)(j + 1), hi);
+        int c01 = 0, c23 = 0;                       // two 16-bit counters per word (a tile holds < 2^15 keys)
+        int c[4] = {0, 0, 0, 0};
         for (int t = 0; t < n_tiles; ++t) {
             const int n = n_tiles == 1 ? n0 : stage(t);
             int b, e;
             chunk_of(n, b, e);
-            for (int i = b; i < e; ++i) c += skeys[i] >= mid ? 1 : 0;
+            c01 = 0; c23 = 0;
+#pragma unroll 8
+            for (int i = b; i < e; ++i) {
+                const unsigned long long u = skeys[i];
+                c01 += (u >= m[0] ? 1 : 0) + (u >= m[1] ? 0x10000 : 0);
+                c23 += (u >= m[2] ? 1 : 0) + (u >= m[3] ? 0x10000 : 0);
+            }
+            // block totals of both packed words in one barrier
+            const int w01 = __reduce_add_sync(0xffffffffu, c01), w23 = __reduce_add_sync(0xffffffffu, c23);
+            if ((tid & 31) == 0) { sh.red[slot * 2 * WARPS + (tid >> 5)] = w01; sh.red[slot * 2 * WARPS + WARPS + (tid >> 5)] = w23; }
+            __syncthreads();
+            int s01 = 0, s23 = 0;
+#pragma unroll
+            for (int i = 0; i < WARPS; ++i) { s01 += sh.red[slot * 2 * WARPS + i]; s23 += sh.red[slot * 2 * WARPS + WARPS + i]; }
+            slot ^= 1;
+            c[0] += s01 & 0xffff; c[1] += (unsigned)s01 >> 16; c[2] += s23 & 0xffff; c[3] += (unsigned)s23 >> 16;
         }
-        c = block_sum(c, sh.red, slot);
-        slot ^= 1;
-        if (c == k) { theta = mid; exact = true; break; }
-        if (c > k) lo = mid; else hi = mid - 1;
+        int j_gt = -1;                               // largest j with count(u >= m[j]) > k
+        bool hit = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (c[j] == k && !hit) { theta = m[j]; hit = true; }
+            if (c[j] > k) j_gt = j;
+        }
+        if (hit) { exact = true; break; }
+        const unsigned long long new_hi = j_gt < 3 ? m[j_gt + 1] - 1 : hi;
+        if (j_gt >= 0) lo = m[j_gt];
+        hi = new_hi;
     }
+    if (tid == 0) { const long long t1 = clock64(); prof[1] += t1 - t0; t0 = t1; prof[7] += steps; }
     // ---- ordered compaction: keys > theta, then the lowest ids among keys == theta ----
     int need_eq = 0;
     if (!exact) {
@@ -197,6 +247,7 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
             const int n = n_tiles == 1 ? n0 : stage(t);
             int b, e;
             chunk_of(n, b, e);
+#pragma unroll 8
             for (int i = b; i < e; ++i) c += skeys[i] > theta ? 1 : 0;
         }
         c = block_sum(c, sh.red, slot);
@@ -211,6 +262,7 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
         int b, e;
         chunk_of(n, b, e);
         int cg = 0, ce = 0;
+#pragma unroll 8
         for (int i = b; i < e; ++i) {
             const unsigned long long u = skeys[i];
             if (exact) cg += u >= theta ? 1 : 0;
@@ -252,6 +304,7 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
             a.tree.first_child[leaf] = c0;
             a.tree.meta[leaf] = meta | (n << 8);
             a.keys[leaf] = -INFINITY;
+            if (resident) skeys[leaf] = ABSENT;
             int q = 0;
             for (int act_i = 0; act_i < MAX_BRANCH; ++act_i) {
                 int act;
@@ -282,6 +335,7 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
         c->wave_children = run;
         c->n_nodes = n_nodes + run;
         c->n_expanded = n_expanded + k;
+        prof[2] += clock64() - t0;
     }
     return run;
 }
@@ -326,7 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
     extern __shared__ unsigned long long skeys[];
     __shared__ SelShared sh;
     __shared__ float hw_scratch[GROUPS][hw::SCRATCH_FLOATS];
-    __shared__ int s_children, s_nodes, s_expanded;
+    __shared__ int s_nodes, s_expanded, s_staged;
     const int tid = threadIdx.x, lane = tid & 31, li = tid & 15;
     const unsigned n_ctas = gridDim.x;
     Control* ctl = a.ctl;
@@ -346,23 +400,28 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
             tr.meta[0] = 0xff | (avail << 24);
             tr.reward[0] = 0.0; tr.lower[0] = 0.0; tr.upper[0] = 0.0;
             a.keys[0] = 0.0;
-            s_nodes = 1; s_expanded = 0;
+            s_nodes = 1; s_expanded = 0; s_staged = 0;
         }
         __syncthreads();
     }
+    long long tp = clock64();
+    auto lap = [&](int slot) {
+        if (blockIdx.x == 0 && tid == 0) { const long long t1 = clock64(); ctl->prof[slot] += t1 - tp; tp = t1; }
+    };
     // ------------------------------------------------------------------ waves
     while (true) {
         if (blockIdx.x == 0) {
-            const int nn = s_nodes, ne = s_expanded;
+            const int nn = s_nodes, ne = s_expanded, ns = s_staged;
             __syncthreads();
-            const int children = select_wave(a, sh, skeys, nn, ne);
+            const int children = select_wave(a, sh, skeys, nn, ne, ns, ctl->prof);
             if (tid == 0) {
-                s_children = children;
                 if (children == 0) ctl->stop = 1;
-                else { s_nodes = ctl->n_nodes; s_expanded = ctl->n_expanded; }
+                else { s_staged = nn; s_nodes = ctl->n_nodes; s_expanded = ctl->n_expanded; }
+                tp = clock64();
             }
         }
         grid_barrier(ctl, n_ctas);
+        lap(3);
         if (*(volatile int*)&ctl->stop) break;
         const int total = *(volatile int*)&ctl->wave_children;
         const int base = *(volatile int*)&ctl->wave_base;
@@ -399,7 +458,9 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
                 write_child(a, c, leaf, action, m.reward[(int64_t)s * m.n_actions + action], m.terminal[s] != 0, 0);
             }
         }
+        lap(4);
         grid_barrier(ctl, n_ctas);
+        lap(5);
         if (*(volatile int*)&ctl->error) break;
     }
     if (blockIdx.x != 0) return;
@@ -453,6 +514,8 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
         res[5] = len;
         res[6] = tie_node;
         res[7] = n_waves;
+        ctl->prof[6] += clock64() - tp;
+        for (int i = 0; i < 8; ++i) res[8 + i] = (int32_t)(i == 7 ? ctl->prof[i] : ctl->prof[i] >> 8);   // 256-cycle units
     }
 }
 

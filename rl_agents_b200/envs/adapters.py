@@ -28,3 +28,23 @@ def describe(env):
         return d
     raise TypeError("rl_agents_b200 planners need a HighwayLiteEnv or a finite-MDP env "
                     "(got %r); see INTEGRATION.md for the env hand-off" % type(u).__name__)
+
+
+def mdp_fingerprint(mdp):
+    """Cache key of the device copy of a finite MDP's tables: shapes, buffer addresses and a strided
+    checksum -- so that a copying preprocessor (a new but identical mdp object per decision) reuses the
+    device tables, and an mdp mutated in place or a different one recycled at the same id() does not."""
+    if mdp is None:
+        return None
+    parts = [getattr(mdp, "mode", None)]
+    for name in ("transition", "reward", "terminal", "next"):
+        arr = getattr(mdp, name, None)
+        if arr is None:
+            parts.append(None)
+            continue
+        arr = np.asarray(arr)
+        flat = arr.reshape(-1)
+        stride = max(1, flat.size // 4096)
+        parts.append((arr.shape, str(arr.dtype), float(np.asarray(flat[::stride], dtype=np.float64).sum()),
+                      float(np.asarray(flat[-1:], dtype=np.float64).sum())))
+    return tuple(parts)

@@ -156,3 +156,32 @@ def test_wave_highway_large_budget_multi_tile_vs_c_specification():
     c = c_oracle.opd_plan_wave(words, 200000, 0.8, 1024)
     res = c_check(eng, c)
     assert int(res[0, 7]) == c["n_waves"]
+
+
+def test_agent_wavefront_option_matches_the_specification_and_reuses_tables():
+    """`"wavefront": K` in the agent config: same plan as the specification; a copying preprocessor (a new
+    but identical mdp object per decision) does not rebuild the device tables."""
+    from rl_agents_b200.agents.tree_search.deterministic import DeterministicPlannerAgent
+    from rl_agents_b200.envs import FiniteMDPEnv, HighwayLiteEnv
+    env = FiniteMDPEnv(M["large1_T"], M["large1_R"], M["large1_term"])
+    agent = DeterministicPlannerAgent(env, {"budget": 500, "gamma": 0.9, "wavefront": 16})
+    agent.seed(0)
+    plan, _ = planners.opd_plan_wavefront(oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"]), 500, 0.9,
+                                          16, np_random=np_random(0))
+    assert agent.plan(None) == plan
+    eng = agent.planner.engine
+    env2 = FiniteMDPEnv(M["large1_T"].copy(), M["large1_R"].copy(), M["large1_term"].copy())
+    agent.env = env2
+    agent.plan(None)
+    assert agent.planner.engine is eng
+    env3 = FiniteMDPEnv(M["large1_T"].copy(), M["large1_R"] * 0.5, M["large1_term"].copy())
+    agent.env = env3
+    agent.plan(None)
+    assert agent.planner.engine is not eng
+    # HighwayLite through the plugin surface
+    henv = HighwayLiteEnv(seed=4)
+    agent = DeterministicPlannerAgent(henv, {"budget": 400, "gamma": 0.8, "wavefront": 32,
+                                             "env_preprocessors": [{"method": "simplify"}]})
+    agent.seed(0)
+    plan, _ = planners.opd_plan_wavefront(oenvs.HighwayLite(seed=4), 400, 0.8, 32, np_random=np_random(0))
+    assert agent.plan(henv.observation()) == plan
