@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--ref-plans", type=int, default=2, help="--impl reference: whole plan()s per process in the timed steps")
     ap.add_argument("--ref-time-box", type=float, default=420.0, help="--impl reference: stop after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the auxiliary paths (VI C4, MCTS C3, one-decision latency)")
     return ap.parse_args()
 
 
@@ -390,6 +391,8 @@ def run_b200(a):
     dev_scenes = [h.to(dev) for h in host_scenes]
     stream = torch.cuda.current_stream()
 
+    per_rank_ms = []
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -405,7 +408,12 @@ def run_b200(a):
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
+            every = torch.empty(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(every, ms)
+            per_rank_ms[:] = every.cpu().tolist()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        else:
+            per_rank_ms[:] = [float(ms.item())]
         barrier()
         return float(ms.item())
 
@@ -419,6 +427,8 @@ def run_b200(a):
         sampler.start()
     ms = timed(device_step, a.steps)
     clocks = sampler.stop() if rank == 0 else None
+    headline_per_rank = {"min_ms": min(per_rank_ms) / a.steps, "mean_ms": sum(per_rank_ms) / len(per_rank_ms) / a.steps,
+                         "max_ms": max(per_rank_ms) / a.steps, "per_rank_ms_per_step": [x / a.steps for x in per_rank_ms]}
     # sanity: the timed work really is the full search
     res = eng.result.cpu().numpy()
     assert (res[:, 0] > n_exp).all() and (res[:, 4] == 0).all()
@@ -502,6 +512,7 @@ def run_b200(a):
                 "d2h_bytes_per_step": int(plan_host.numel() + res_host.numel() * 4), "ms_per_step": ms_e2e / a.steps,
                 "path": "b2_opd_plan_host (C ABI, host buffers, synchronous); wall clock over the steps, max over ranks"},
         "gpu_launches": a.steps,
+        "per_rank": headline_per_rank,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "opd_highway_multi_kernel",
@@ -509,7 +520,13 @@ def run_b200(a):
                      "note": "latency/FP32-issue bound by construction (15 dependent sub-steps per child); "
                              "HBM fraction reported as the contract asks, see DESIGN.md section 4"},
     }
-    if rank == 0:
+    if not a.headline_only:
+        try:
+            extra = other_paths(a, dev, world, rank)           # collective calls inside: every rank takes part
+        except Exception as e:
+            extra = {"error": repr(e)[:300]}
+        out["other_paths"] = extra
+    if rank == 0 and not a.headline_only:
         try:
             out["single_decision"] = single_decision_latency(a, dev)
         except Exception as e:          # an auxiliary measurement must never take the headline down
@@ -524,6 +541,184 @@ def run_b200(a):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_paths(a, dev, world, rank):
+    """The other BASELINE paths through the same launch (driver-visible evidence for SURVEY 8e): C4 value
+    iteration slab-sharded over the ranks (the path's one exchange step timed next to the compute), C3 MCTS
+    root-parallel with its single [2, A] all-reduce, and one budget-1e6 OPD decision sub-tree sharded.  Every
+    time is CUDA events / device-synchronised wall clock, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from rl_agents_b200 import _lib
+    from rl_agents_b200 import distributed as D
+    from rl_agents_b200.engine.vi import VIEngine
+    from rl_agents_b200.envs.finite_mdp import garnet_slab
+    from rl_agents_b200.envs.highway_lite import make_scene
+    out = {}
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_ms(fn, reps=3):
+        best = None
+        for _ in range(reps):
+            sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            best = ms if best is None else min(best, ms)
+        return best
+
+    peak = 6650.0
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+    except Exception:
+        pass
+    # ---- C4: value iteration, S = 1e6, A = 8, B = 4 sparse, 100 sweeps, early exit off (rtol 0, atol -1) ----
+    try:
+        S, A, B, sweeps = 1000000, 8, 4, 100
+        b, e = D.shard_range(S, rank, world)
+        P, N, R, term = garnet_slab(S, A, B, b, e, seed=0, device=dev)
+        if world > 1:
+            vi = D.DistributedVI("sparse", P, R, term, nxt=N, gamma=0.95, device=dev, tables_are_local=True,
+                                 n_states=S, check_every=10, rtol=0.0, atol=-1.0)
+            full = timed_ms(lambda: vi.solve(sweeps))
+            comp = timed_ms(lambda: vi.solve(sweeps, exchange=False))
+            eng = vi.engine
+        else:
+            eng = VIEngine("sparse", P, R, term, nxt=N, gamma=0.95, device=dev, rtol=0.0, atol=-1.0)
+            full = timed_ms(lambda: eng.solve(sweeps))
+            comp = full
+        algo = float(S * A * B * 20 + S * A * 24 + S * 9)            # whole MDP, bytes per sweep (SURVEY 8d + Q_old)
+        # cold-L2 variant on one GPU: alternate between two table sets (2 x 0.8 GB >> 126 MB L2)
+        cold = None
+        if world == 1:
+            P2, N2, R2, term2 = garnet_slab(S, A, B, 0, S, seed=1, device=dev)
+            eng2 = VIEngine("sparse", P2, R2, term2, nxt=N2, gamma=0.95, device=dev, rtol=0.0, atol=-1.0)
+            eng.reset(sweeps)
+            eng2.reset(sweeps)
+
+            def alternate():
+                for k in range(sweeps // 2):
+                    eng.sweep(k)
+                    eng2.sweep(k)
+            cold = timed_ms(alternate)
+            del eng2, P2, N2, R2
+        out["vi_c4"] = {
+            "workload": "C4: Bellman sweeps, garnet sparse MDP S=1e6 A=8 B=4 fp64/int32, gamma 0.95, %d sweeps, "
+                        "early exit off, state slabs over %d GPU(s)" % (sweeps, world),
+            "sweeps_per_s": sweeps / (full * 1e-3), "us_per_sweep": 1e3 * full / sweeps,
+            "us_per_sweep_compute_only": 1e3 * comp / sweeps,
+            "us_per_sweep_exchange": 1e3 * (full - comp) / sweeps,
+            "exchange": None if world == 1 else "all_gather of the V slabs (%.1f MB per rank per sweep) every sweep + "
+                        "all_reduce of 10 violation counters every 10 sweeps (NCCL)" % (8.0 * S / world / 1e6),
+            "roofline": {"bound": "hbm", "achieved": algo / (full * 1e-3 / sweeps) / 1e9, "peak": peak * world,
+                         "unit": "GB/s", "frac": algo / (full * 1e-3 / sweeps) / 1e9 / (peak * world),
+                         "algorithmic_bytes_per_sweep": algo, "kernel": "vi_sweep_row_kernel<4,true>"},
+            "cold_l2_us_per_sweep": None if cold is None else 1e3 * cold / (2 * (sweeps // 2)),
+            "cold_l2_frac": None if cold is None else algo / (cold * 1e-3 / (2 * (sweeps // 2))) / 1e9 / peak}
+        del eng, P, N, R
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["vi_c4"] = {"error": repr(ex)[:300]}
+    # ---- C1: dense stochastic VI, S = 100, A = 4 (the reference's CPU-runnable case): launch-latency bound ----
+    try:
+        g = torch.Generator(device=dev)
+        g.manual_seed(0)
+        P1 = torch.rand((100, 4, 100), dtype=torch.float64, device=dev, generator=g)
+        P1 = P1 / P1.sum(dim=-1, keepdim=True)
+        R1 = torch.rand((100, 4), dtype=torch.float64, device=dev, generator=g)
+        e1 = VIEngine("stochastic", P1, R1, torch.zeros(100, dtype=torch.uint8, device=dev), gamma=0.95, device=dev,
+                      rtol=0.0, atol=-1.0)
+        ms = timed_ms(lambda: e1.solve(100))
+        bytes1 = 100 * 4 * 100 * 8 + 100 * 4 * 24 + 100 * 9
+        out["vi_c1"] = {"workload": "C1: dense VI S=100 A=4 fp64, 100 sweeps enqueued back to back (b2_vi_solve)",
+                        "us_per_sweep": 1e3 * ms / 100,
+                        "roofline": {"bound": "hbm", "achieved": bytes1 / (ms * 1e-3 / 100) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": bytes1 / (ms * 1e-3 / 100) / 1e9 / peak, "algorithmic_bytes_per_sweep": bytes1,
+                                     "note": "0.32 MB per sweep lives in L2; the sweep is bound by kernel launch latency"}}
+    except Exception as ex:
+        out["vi_c1"] = {"error": repr(ex)[:300]}
+    # ---- C3: MCTS 4096 episodes x horizon 20, root-parallel: 64 trees of 64 episodes over all ranks ----
+    try:
+        from rl_agents_b200.engine.mcts import MCTSEngine, pcg64_words
+        total_trees, episodes, horizon = 64, 64, 20
+        mine = [t for t in range(total_trees) if t % world == rank]
+        eng = MCTSEngine(_lib.ENV_HIGHWAY, len(mine), N_ACTIONS, episodes, horizon, 0.8, 10.0, device=dev)
+        scene = torch.tensor(make_scene(0), dtype=torch.int32, device=dev)
+        roots = scene.repeat(len(mine), 1).contiguous()
+        gens = np.random.Generator(np.random.PCG64(np.random.SeedSequence(0))).spawn(total_trees)
+        words = np.stack([pcg64_words(gens[t]) for t in mine])
+        merged = {}
+
+        def decide(collective=True):
+            eng.plan(roots, words)
+            fc = eng.first_child[:, 0]
+            idx = fc.long().unsqueeze(1) + torch.arange(N_ACTIONS, device=dev).unsqueeze(0)
+            nch = (eng.meta[:, 0] >> 8) & 0xff
+            valid = torch.arange(N_ACTIONS, device=dev).unsqueeze(0) < nch.unsqueeze(1)
+            idx = torch.where(valid, idx, torch.zeros_like(idx))
+            acts = (torch.gather(eng.meta, 1, idx) & 0xff).long()
+            cnt = torch.where(valid, torch.gather(eng.count, 1, idx), torch.zeros_like(idx, dtype=torch.int32)).double()
+            val = torch.where(valid, torch.gather(eng.value, 1, idx), torch.zeros_like(cnt))
+            acts = torch.where(valid, acts, torch.zeros_like(acts))
+            counts = torch.zeros(N_ACTIONS, dtype=torch.float64, device=dev).scatter_add_(0, acts.reshape(-1), cnt.reshape(-1))
+            sums = torch.zeros(N_ACTIONS, dtype=torch.float64, device=dev).scatter_add_(0, acts.reshape(-1), (cnt * val).reshape(-1))
+            values = torch.where(counts > 0, sums / counts.clamp(min=1), torch.zeros_like(sums))
+            if collective and world > 1:
+                counts, values = D.merge_root_statistics(counts, values)
+            merged["c"], merged["v"] = counts, values
+        full = timed_ms(decide)
+        comp = timed_ms(lambda: decide(False))
+        c, v = merged["c"].cpu().numpy(), merged["v"].cpu().numpy()
+        out["mcts_c3_root_parallel"] = {
+            "workload": "C3: MCTS on HighwayLite, 4096 episodes x horizon 20 as 64 root-parallel trees of 64 episodes "
+                        "(strict episode order inside each tree), trees dealt over %d GPU(s)" % world,
+            "ms_per_decision": full, "ms_compute_only": comp, "ms_collective": full - comp,
+            "collective": None if world == 1 else "one all_reduce of the root's [2, A] (count, count*value)",
+            "episodes_per_s": 4096 / (full * 1e-3), "env_steps_upper_bound_per_s": 4096 * horizon / (full * 1e-3),
+            "recommended_action": int(D.recommend(c, v)), "root_counts": c.tolist()}
+        del eng
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["mcts_c3_root_parallel"] = {"error": repr(ex)[:300]}
+    # ---- C5-sized: ONE OPD decision, budget 1e6, sub-tree sharded (ShardedOPD, one all_reduce(MAX)) ----
+    try:
+        sh = D.ShardedOPD(1000000, 0.8, device=dev)
+        scene_np = make_scene(0)
+        sync()
+        t0 = time.perf_counter()
+        r = sh.decide(scene_np)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        sync()
+        t0 = time.perf_counter()
+        r = sh.decide(scene_np)
+        torch.cuda.synchronize()
+        dt = min(dt, max_over_ranks(time.perf_counter() - t0))
+        out["opd_1e6_subtree_sharded"] = {
+            "workload": "ONE OPD decision on HighwayLite (C5's env intersection-v0 is not modelled), budget 1e6, gamma 0.8, "
+                        "%d sub-trees dealt over %d GPU(s), strict best-first inside each" % (r["n_subtrees"], world),
+            "s_per_decision": dt, "expansions_per_s": 200000 / dt, "action": int(r["action"]),
+            "root_lower": float(r["root_lower"]),
+            "collective": None if world == 1 else "one all_reduce(MAX) of the [n_subtrees, 2] bounds"}
+    except Exception as ex:
+        out["opd_1e6_subtree_sharded"] = {"error": repr(ex)[:300]}
+    return out
 
 
 def single_decision_latency(a, dev, reps=5):

@@ -55,32 +55,65 @@ def allgather_slabs(full, n, group=None):
 
 
 class DistributedVI(object):
-    """Slab-sharded value iteration (value_iteration.py:42-73 over G GPUs)."""
+    """Slab-sharded value iteration (value_iteration.py:42-73 over G GPUs): rank g owns rows
+    [g*S/G, (g+1)*S/G) of P / N / R / Q and needs the whole V for its gathers, so the path has ONE exchange
+    step per sweep: the all-gather of the V slabs.  The allclose violation counters (one int per sweep) are
+    all-reduced every `check_every` sweeps as a vector: 1 (default) keeps the reference's early exit exactly
+    (the sweep after the converged one does nothing and the OLD iterate is returned); a larger value trades
+    that for fewer collectives -- sweeps then continue up to the next check, and the result is the iterate
+    at the first converged sweep only if it is still in the ping-pong buffers (otherwise the latest one,
+    which differs from it by less than the allclose tolerance).
+
+    tables_are_local=False: `transition/reward/terminal/nxt` are the FULL host tables and every rank slices its
+    slab (small MDPs, tests).  tables_are_local=True: they are already this rank's slab (rows
+    shard_range(n_states, rank, world)), host arrays or device tensors -- no rank ever materialises another
+    rank's rows (C4: 640 MB of P/N per GPU instead of 5 GB each)."""
 
     def __init__(self, mode, transition, reward, terminal, nxt=None, gamma=1.0, device="cuda", group=None,
-                 tables_are_local=False):
+                 tables_are_local=False, n_states=None, check_every=1, rtol=1e-5, atol=1e-8):
         import torch.distributed as dist
         from rl_agents_b200.engine.vi import VIEngine
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.check_every = max(1, int(check_every))
         if tables_are_local:
-            raise NotImplementedError
-        S = np.asarray(reward).shape[0]
+            if n_states is None:
+                raise ValueError("tables_are_local needs n_states (the whole MDP's state count)")
+            S = int(n_states)
+            b, e = shard_range(S, self.rank, self.world)
+            if int(reward.shape[0]) != e - b:
+                raise ValueError("rank %d owns rows [%d, %d) but got %d rows" % (self.rank, b, e, reward.shape[0]))
+            slab = (transition, reward, terminal, nxt)
+        else:
+            S = np.asarray(reward).shape[0]
+            b, e = shard_range(S, self.rank, self.world)
+            slab = (np.asarray(transition)[b:e], np.asarray(reward)[b:e], np.asarray(terminal)[b:e],
+                    None if nxt is None else np.asarray(nxt)[b:e])
         self.n_states = S
-        b, e = shard_range(S, self.rank, self.world)
-        self.engine = VIEngine(mode, np.asarray(transition)[b:e], np.asarray(reward)[b:e], np.asarray(terminal)[b:e],
-                               nxt=None if nxt is None else np.asarray(nxt)[b:e], gamma=gamma, device=device,
-                               row_begin=b, row_end=e, n_states=S)
+        self.engine = VIEngine(mode, slab[0], slab[1], slab[2], nxt=slab[3], gamma=gamma, device=device,
+                               row_begin=b, row_end=e, n_states=S, rtol=rtol, atol=atol)
 
-    def solve(self, iterations):
-        """Returns (this rank's Q slab on device, sweeps).  No host sync inside the loop:
-        the sweep kernels read the all-reduced violation counters from device memory."""
+    def solve(self, iterations, exchange=True):
+        """Returns (this rank's Q slab on device, sweeps).  No host sync inside the loop: the sweep kernels
+        read the all-reduced violation counters from device memory.  exchange=False skips the collectives
+        (timing of the compute alone; the values are then meaningless)."""
         eng = self.engine
         eng.reset(iterations)
+        m = self.check_every
+        if m > 1 or not exchange:
+            # a rank whose own slab shows 0 violations must keep sweeping until the GLOBAL count is known:
+            # bias every local counter by one (removed again after the all-reduce)
+            eng.viol.fill_(1)
         for k in range(iterations):
             eng.sweep(k)
+            if not exchange:
+                continue
             allgather_slabs(eng.v[(k + 1) & 1], self.n_states, self.group)
-            self.dist.all_reduce(eng.viol[k:k + 1], group=self.group)
+            if (k + 1) % m == 0 or k + 1 == iterations:
+                k0 = (k // m) * m
+                self.dist.all_reduce(eng.viol[k0:k + 1], group=self.group)
+                if m > 1:
+                    eng.viol[k0:k + 1] -= self.world
         return eng.result(iterations)
 
 
@@ -95,6 +128,34 @@ def merge_root_statistics(counts, values, group=None):
     merged_counts = packed[0]
     merged_values = torch.where(merged_counts > 0, packed[1] / merged_counts.clamp(min=1), torch.zeros_like(packed[1]))
     return merged_counts, merged_values
+
+
+def merge_olop_root_statistics(counts, uppers, group=None):
+    """OLOP root parallelisation: every rank runs its share of the episodes on its own
+    sequence tree from the same root; the recommendation (OLOPNode.selection_rule, olop.py:126-130: most
+    visited child, ties -> largest value_upper) is taken on the merged root statistics -- counts summed,
+    value_upper = the tightest bound any rank holds for that action (min over the ranks that tried it).
+    ONE all-gather of [2, A]; returns (counts, uppers) on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.stack([counts.to(torch.float64), uppers.to(torch.float64)]).contiguous()
+    flat = torch.empty(world * mine.numel(), dtype=torch.float64, device=mine.device)
+    dist.all_gather_into_tensor(flat, mine.reshape(-1), group=group)
+    out = flat.reshape((world,) + tuple(mine.shape))
+    merged_counts = out[:, 0].sum(dim=0)
+    tried = out[:, 0] > 0
+    inf = torch.full_like(out[:, 1], float("inf"))
+    best_upper = torch.where(tried, out[:, 1], inf).min(dim=0).values
+    merged_uppers = torch.where(merged_counts > 0, best_upper, out[:, 1].max(dim=0).values)
+    return merged_counts, merged_uppers
+
+
+def recommend_olop(counts, uppers):
+    """OLOPNode.selection_rule (olop.py:126-130) on merged statistics."""
+    counts, uppers = np.asarray(counts), np.asarray(uppers)
+    ties = np.nonzero(counts == counts.max())[0]
+    return int(max(ties, key=lambda i: uppers[i]))
 
 
 def recommend(counts, values):

@@ -18,7 +18,15 @@ class VIEngine(object):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.mode = mode
-        reward = np.asarray(reward, dtype=np.float64)
+
+        def dev(x, dtype):
+            """host arrays are uploaded; tensors already on the device (slabs generated / loaded in place,
+            rl_agents_b200.distributed tables_are_local) are used as they are."""
+            if isinstance(x, torch.Tensor):
+                return x.to(device=self.device, dtype=dtype).contiguous()
+            np_dtype = {torch.int32: np.int32, torch.float64: np.float64, torch.uint8: np.uint8}[dtype]
+            return torch.as_tensor(np.ascontiguousarray(x, dtype=np_dtype), device=self.device)
+        reward = dev(reward, torch.float64)
         rows, A = reward.shape
         self.n_actions = A
         self.n_states = int(n_states if n_states is not None else rows)
@@ -26,19 +34,19 @@ class VIEngine(object):
         self.row_end = int(row_end if row_end is not None else self.row_begin + rows)
         assert self.row_end - self.row_begin == rows
         if mode == "deterministic":
-            self.transition = torch.as_tensor(np.ascontiguousarray(transition, dtype=np.int32), device=self.device)
+            self.transition = dev(transition, torch.int32)
             self.next, self.n_next = None, 1
         elif mode == "stochastic":
-            self.transition = torch.as_tensor(np.ascontiguousarray(transition, dtype=np.float64), device=self.device)
+            self.transition = dev(transition, torch.float64)
             self.next, self.n_next = None, self.n_states
         elif mode == "sparse":
-            self.transition = torch.as_tensor(np.ascontiguousarray(transition, dtype=np.float64), device=self.device)
-            self.next = torch.as_tensor(np.ascontiguousarray(nxt, dtype=np.int32), device=self.device)
+            self.transition = dev(transition, torch.float64)
+            self.next = dev(nxt, torch.int32)
             self.n_next = int(self.next.shape[-1])
         else:
             raise ValueError("Unknown mode")
-        self.reward = torch.as_tensor(np.ascontiguousarray(reward), device=self.device)
-        self.terminal = torch.as_tensor(np.ascontiguousarray(terminal, dtype=np.uint8), device=self.device)
+        self.reward = reward
+        self.terminal = dev(terminal, torch.uint8)
         self.problem = _lib.VIProblem(MODES[mode], A, self.n_next, 0, self.n_states, self.row_begin, self.row_end,
                                       float(gamma), rtol, atol, self.transition.data_ptr(),
                                       self.next.data_ptr() if self.next is not None else None,

@@ -73,3 +73,34 @@ class FiniteMDPEnv(object):
         # the `finite_mdp` package's MDP.step evaluates done on the state the action was taken IN
         # (consistent with value_iteration.py:62, which zeroes the next-value of terminal SOURCE states)
         return s2, r, bool(m.terminal[s]), False, {}
+
+
+def garnet_slab(n_states, n_actions, n_next, row_begin, row_end, seed=0, device="cuda", reward_sparsity=0.5):
+    """Rows [row_begin, row_end) of a garnet-style sparse MDP, generated ON the device, slab by
+    slab (rows are seeded independently, so any partition of the rows yields the same MDP): successors uniform
+    over the states, P = normalised U(0,1), R ~ U(0,1) with `reward_sparsity` of the entries zeroed, no
+    terminal states.  Returns (P f64 [rows,A,B], N i32 [rows,A,B], R f64 [rows,A], terminal u8 [rows])."""
+    import torch
+    dev = torch.device(device)
+    rows = int(row_end) - int(row_begin)
+    chunk = 65536                                    # rows per seeded block: slabs need not align with blocks
+    P = torch.empty((rows, n_actions, n_next), dtype=torch.float64, device=dev)
+    N = torch.empty((rows, n_actions, n_next), dtype=torch.int32, device=dev)
+    R = torch.empty((rows, n_actions), dtype=torch.float64, device=dev)
+    first = (int(row_begin) // chunk) * chunk
+    for b0 in range(first, int(row_end), chunk):
+        g = torch.Generator(device=dev)
+        g.manual_seed(int(seed) * 1000003 + b0 // chunk)
+        n = min(chunk, int(n_states) - b0)
+        p = torch.rand((n, n_actions, n_next), dtype=torch.float64, device=dev, generator=g)
+        nx = torch.randint(0, int(n_states), (n, n_actions, n_next), dtype=torch.int32, device=dev, generator=g)
+        r = torch.rand((n, n_actions), dtype=torch.float64, device=dev, generator=g)
+        keep = torch.rand((n, n_actions), dtype=torch.float64, device=dev, generator=g) >= reward_sparsity
+        lo, hi = max(b0, int(row_begin)), min(b0 + n, int(row_end))
+        if lo >= hi:
+            continue
+        src, dst = slice(lo - b0, hi - b0), slice(lo - int(row_begin), hi - int(row_begin))
+        P[dst] = p[src] / p[src].sum(dim=-1, keepdim=True)
+        N[dst] = nx[src]
+        R[dst] = r[src] * keep[src]
+    return P, N, R, torch.zeros(rows, dtype=torch.uint8, device=dev)

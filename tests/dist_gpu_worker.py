@@ -34,6 +34,18 @@ def main():
     b, e = shard_range(S, rank, world)
     out["vi_ok"] = bool(np.array_equal(q.cpu().numpy(), q_ref[b:e])) and sweeps == sweeps_ref
     out["vi_sweeps"] = sweeps
+    # --- tables_are_local: every rank hands over only its own slab, as device tensors ---
+    slab = dict(transition=torch.as_tensor(P[b:e]).to(dev), reward=torch.as_tensor(R[b:e]).to(dev),
+                terminal=torch.as_tensor(term[b:e].astype(np.uint8)).to(dev),
+                nxt=torch.as_tensor(N[b:e].astype(np.int32)).to(dev))
+    dvi2 = DistributedVI("sparse", gamma=0.6, device=dev, tables_are_local=True, n_states=S, **slab)
+    q2, sweeps2 = dvi2.solve(80)
+    out["vi_local_ok"] = bool(np.array_equal(q2.cpu().numpy(), q_ref[b:e])) and sweeps2 == sweeps_ref
+    # violation counters exchanged every 4 sweeps: same fixed point within the allclose tolerance
+    dvi3 = DistributedVI("sparse", gamma=0.6, device=dev, tables_are_local=True, n_states=S, check_every=4, **slab)
+    q3, sweeps3 = dvi3.solve(80)
+    out["vi_check_every_ok"] = bool(np.allclose(q3.cpu().numpy(), q_ref[b:e], rtol=1e-4, atol=1e-7)) \
+        and sweeps_ref <= sweeps3 <= sweeps_ref + 4
     # --- root-parallel MCTS: one all-reduce of root statistics ---
     words = oenvs.make_highway_state(3).pack()
     ss = np.random.SeedSequence(11).spawn(world)[rank]

@@ -121,3 +121,21 @@ def test_root_parallel_merge_and_recommendation():
     assert v == pytest.approx([(10 * 1.0 + 2 * 4.0) / 12, 0.0, (5 * 2.0 + 13 * 1.0) / 18])
     assert recommend(c, v) == 2
     assert recommend([5, 5, 1], [0.1, 0.7, 9.0]) == 1
+
+
+def _olop_merge_case(rank, world):
+    from rl_agents_b200.distributed import merge_olop_root_statistics
+    counts = torch.tensor([[4, 0, 6, 0], [5, 0, 3, 0]][rank], dtype=torch.int32)
+    uppers = torch.tensor([[2.5, 9.0, 3.0, 9.0], [2.0, 9.0, 3.5, 9.0]][rank], dtype=torch.float64)
+    c, u = merge_olop_root_statistics(counts, uppers)
+    return c.tolist(), u.tolist()
+
+
+def test_olop_root_parallel_merge_and_recommendation():
+    from rl_agents_b200.distributed import recommend_olop
+    out = run_world(_olop_merge_case)
+    assert out[0] == out[1]
+    c, u = out[0]
+    assert c == [9.0, 0.0, 9.0, 0.0]
+    assert u == [2.0, 9.0, 3.0, 9.0]          # tightest bound among the ranks that tried the action
+    assert recommend_olop(c, u) == 2           # equal counts: larger value_upper (olop.py:126-130)
