@@ -596,13 +596,23 @@ def other_paths(a, dev, world, rank):
         if world > 1:
             vi = D.DistributedVI("sparse", P, R, term, nxt=N, gamma=0.95, device=dev, tables_are_local=True,
                                  n_states=S, check_every=10, rtol=0.0, atol=-1.0)
-            full = timed_ms(lambda: vi.solve(sweeps))
+            nccl_full = timed_ms(lambda: vi.solve(sweeps))
             comp = timed_ms(lambda: vi.solve(sweeps, exchange=False))
             eng = vi.engine
+            p2p_full, p2p_err = None, None
+            try:
+                vi2 = D.DistributedVI("sparse", P, R, term, nxt=N, gamma=0.95, device=dev, tables_are_local=True,
+                                      n_states=S, rtol=0.0, atol=-1.0, exchange="p2p", max_iterations=sweeps)
+                p2p_full = timed_ms(lambda: vi2.solve(sweeps))
+                vi2.close()
+                del vi2
+            except Exception as ex:
+                p2p_err = repr(ex)[:200]
+            full = nccl_full if p2p_full is None else min(nccl_full, p2p_full)
         else:
             eng = VIEngine("sparse", P, R, term, nxt=N, gamma=0.95, device=dev, rtol=0.0, atol=-1.0)
             full = timed_ms(lambda: eng.solve(sweeps))
-            comp = full
+            comp, nccl_full, p2p_full, p2p_err = full, None, None, None
         algo = float(S * A * B * 20 + S * A * 24 + S * 9)            # whole MDP, bytes per sweep (SURVEY 8d + Q_old)
         # cold-L2 variant on one GPU: alternate between two table sets (2 x 0.8 GB >> 126 MB L2)
         cold = None
@@ -624,8 +634,15 @@ def other_paths(a, dev, world, rank):
             "sweeps_per_s": sweeps / (full * 1e-3), "us_per_sweep": 1e3 * full / sweeps,
             "us_per_sweep_compute_only": 1e3 * comp / sweeps,
             "us_per_sweep_exchange": 1e3 * (full - comp) / sweeps,
-            "exchange": None if world == 1 else "all_gather of the V slabs (%.1f MB per rank per sweep) every sweep + "
-                        "all_reduce of 10 violation counters every 10 sweeps (NCCL)" % (8.0 * S / world / 1e6),
+            "exchange": None if world == 1 else {
+                "nccl_us_per_sweep": 1e3 * nccl_full / sweeps,
+                "nccl": "sweep kernel, then all_gather of the V slabs (%.1f MB per rank) every sweep + all_reduce of "
+                        "10 violation counters every 10 sweeps" % (8.0 * S / world / 1e6),
+                "p2p_us_per_sweep": None if p2p_full is None else 1e3 * p2p_full / sweeps,
+                "p2p": "b2_vi_sweep_p2p: V' stored into every rank's copy over NVLink inside the sweep kernel, "
+                       "violation counts + arrival flags published by the last CTA; no collective call, exact "
+                       "per-sweep early-exit protocol" if p2p_err is None else "failed: " + p2p_err,
+                "used_for_us_per_sweep": "p2p" if (p2p_full is not None and p2p_full <= nccl_full) else "nccl"},
             "roofline": {"bound": "hbm", "achieved": algo / (full * 1e-3 / sweeps) / 1e9, "peak": peak * world,
                          "unit": "GB/s", "frac": algo / (full * 1e-3 / sweeps) / 1e9 / (peak * world),
                          "algorithmic_bytes_per_sweep": algo, "kernel": "vi_sweep_row_kernel<4,true>"},
@@ -682,8 +699,8 @@ def other_paths(a, dev, world, rank):
             if collective and world > 1:
                 counts, values = D.merge_root_statistics(counts, values)
             merged["c"], merged["v"] = counts, values
-        full = timed_ms(decide)
         comp = timed_ms(lambda: decide(False))
+        full = timed_ms(decide)
         c, v = merged["c"].cpu().numpy(), merged["v"].cpu().numpy()
         out["mcts_c3_root_parallel"] = {
             "workload": "C3: MCTS on HighwayLite, 4096 episodes x horizon 20 as 64 root-parallel trees of 64 episodes "

@@ -102,6 +102,37 @@ int b2_vi_sweep(const b2_vi_problem* p, const double* v_in, const double* q_old,
 int b2_vi_solve(const b2_vi_problem* p, double* q0, double* q1, double* v0, double* v1,
                 int32_t* viol, int32_t iterations, void* stream);
 
+/* ---- slab-sharded value iteration with the exchange fused into the sweep over NVLink peer memory ----
+ * Replaces "sweep; ncclAllGather(V); ncclAllReduce(violations)" of the sharded fixed-point loop
+ * (value_iteration.py:42-73 over G GPUs, one process per GPU): every rank keeps the V ping-pong buffers, an
+ * arrival-flag array [world] and a violation table [iterations, world] in CUDA-IPC shared device memory
+ * (b2_p2p_alloc / export / import); the sweep kernel stores V' into every rank's copy and publishes its count and
+ * flag when its last CTA retires; the next sweep acquires the flags.  No NCCL call inside the loop. */
+#define B2_MAX_PEERS 8
+int b2_p2p_alloc(int64_t bytes, void** ptr);                          /* zeroed, IPC-exportable device memory */
+int b2_p2p_free(void* ptr);
+int b2_p2p_export(void* ptr, unsigned char* handle64);                /* cudaIpcGetMemHandle (64 bytes)        */
+int b2_p2p_import(const unsigned char* handle64, void** peer_ptr);    /* cudaIpcOpenMemHandle + peer access    */
+int b2_p2p_close(void* peer_ptr);
+int b2_p2p_memset(void* ptr, int32_t value, int64_t bytes, void* stream);
+int b2_p2p_read(void* dst_host, const void* src_dev, int64_t bytes, void* stream);   /* synchronous D2H */
+
+typedef struct b2_vi_p2p {
+    int32_t world, rank;
+    double* v[2][B2_MAX_PEERS];      /* v[i][r]: V ping-pong buffer i ([S] doubles) in rank r's memory          */
+    int32_t* flags[B2_MAX_PEERS];    /* flags[r]: rank r's [world] arrival flags; this rank writes flags[r][rank] */
+    int32_t* parts[B2_MAX_PEERS];    /* parts[r]: rank r's [iterations, world] violation table                   */
+    int32_t* viol_local;             /* [iterations] this rank's own counters (local scratch, zeroed)            */
+    uint32_t* done;                  /* [iterations] retired-CTA counters (local scratch, zeroed)                */
+} b2_vi_p2p;
+
+/* Sweep `sweep_index` of the slab [row_begin, row_end): reads v[sweep&1][rank] and q_old, writes q_new and
+ * V' into v[(sweep+1)&1][r] of every rank r.  Sparse / deterministic mode, A a power of two <= 32,
+ * B in {1,2,4,8}.  After synchronising, sum_r parts[rank][k*world + r] is sweep k's allclose violation count
+ * (same convergence protocol as b2_vi_sweep). */
+int b2_vi_sweep_p2p(const b2_vi_problem* p, const b2_vi_p2p* x, const double* q_old, double* q_new,
+                    int32_t sweep_index, void* stream);
+
 /* Robust value iteration (rl_agents/agents/dynamic_programming/robust_value_iteration.py:39-58):
  * Q' = min over n_models models of R_m + gamma * E_m[V(s')], no terminal handling.
  * p->transition: int32 [M,S,A] (deterministic) or double [M,S,A,S] (stochastic);

@@ -34,6 +34,15 @@ class VIProblem(ctypes.Structure):
                 ("transition", c_void_p), ("next", c_void_p), ("reward", c_void_p), ("terminal", c_void_p)]
 
 
+MAX_PEERS = 8
+
+
+class VIP2P(ctypes.Structure):
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("v", (c_void_p * MAX_PEERS) * 2),
+                ("flags", c_void_p * MAX_PEERS), ("parts", c_void_p * MAX_PEERS),
+                ("viol_local", c_void_p), ("done", c_void_p)]
+
+
 class OPDConfig(ctypes.Structure):
     _fields_ = [("env_kind", c_int32), ("n_trees", c_int32), ("n_actions", c_int32),
                 ("n_expansions", c_int32), ("node_capacity", c_int32), ("plan_capacity", c_int32),
@@ -89,6 +98,14 @@ EXPORTS = {
     "b2_vi_sweep": (c_int, [ctypes.POINTER(VIProblem)] + [c_void_p] * 5 + [c_int32, c_void_p]),
     "b2_vi_solve": (c_int, [ctypes.POINTER(VIProblem)] + [c_void_p] * 5 + [c_int32, c_void_p]),
     "b2_vi_robust_sweep": (c_int, [ctypes.POINTER(VIProblem), c_int32] + [c_void_p] * 5 + [c_int32, c_void_p]),
+    "b2_p2p_alloc": (c_int, [c_int64, ctypes.POINTER(c_void_p)]),
+    "b2_p2p_free": (c_int, [c_void_p]),
+    "b2_p2p_export": (c_int, [c_void_p, ctypes.c_char_p]),
+    "b2_p2p_import": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "b2_p2p_close": (c_int, [c_void_p]),
+    "b2_p2p_memset": (c_int, [c_void_p, c_int32, c_int64, c_void_p]),
+    "b2_p2p_read": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "b2_vi_sweep_p2p": (c_int, [ctypes.POINTER(VIProblem), ctypes.POINTER(VIP2P), c_void_p, c_void_p, c_int32, c_void_p]),
     "b2_opd_workspace_bytes": (c_int64, [ctypes.POINTER(OPDConfig)]),
     "b2_opd_plan": (c_int, [ctypes.POINTER(OPDConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
                             c_void_p, c_void_p]),

@@ -54,6 +54,50 @@ def allgather_slabs(full, n, group=None):
     return full
 
 
+class PeerBuffer(object):
+    """A device buffer of `nbytes` per rank that every rank of the group can address (CUDA IPC over
+    NVLink / NVSwitch): `ptrs[r]` is the address of rank r's buffer in THIS process (ptrs[rank] is the
+    local allocation).  One process per GPU on one node."""
+
+    def __init__(self, nbytes, group=None):
+        import ctypes
+        import torch.distributed as dist
+        from rl_agents_b200 import _lib
+        self.lib = _lib.load()
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.nbytes = int(nbytes)
+        local = ctypes.c_void_p()
+        _lib.check(self.lib.b2_p2p_alloc(self.nbytes, ctypes.byref(local)))
+        self.local = local.value
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(self.lib.b2_p2p_export(ctypes.c_void_p(self.local), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.ptrs, self._opened = [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.local)
+                continue
+            peer = ctypes.c_void_p()
+            _lib.check(self.lib.b2_p2p_import(ctypes.create_string_buffer(h, 64), ctypes.byref(peer)))
+            self.ptrs.append(peer.value)
+            self._opened.append(peer.value)
+
+    def close(self):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)           # nobody still writes into a buffer that is about to go
+        for p in self._opened:
+            self.lib.b2_p2p_close(ctypes.c_void_p(p))
+        self._opened = []
+        if self.local:
+            self.lib.b2_p2p_free(ctypes.c_void_p(self.local))
+            self.local = None
+
+
 class DistributedVI(object):
     """Slab-sharded value iteration (value_iteration.py:42-73 over G GPUs): rank g owns rows
     [g*S/G, (g+1)*S/G) of P / N / R / Q and needs the whole V for its gathers, so the path has ONE exchange
@@ -70,12 +114,19 @@ class DistributedVI(object):
     rank's rows (C4: 640 MB of P/N per GPU instead of 5 GB each)."""
 
     def __init__(self, mode, transition, reward, terminal, nxt=None, gamma=1.0, device="cuda", group=None,
-                 tables_are_local=False, n_states=None, check_every=1, rtol=1e-5, atol=1e-8):
+                 tables_are_local=False, n_states=None, check_every=1, rtol=1e-5, atol=1e-8, exchange="nccl",
+                 max_iterations=1024):
+        """exchange="nccl": all-gather / all-reduce collectives after each sweep kernel (also what the gloo CPU
+        tests drive).  exchange="p2p": the exchange is fused into the sweep kernel over NVLink peer memory
+        (b2_vi_sweep_p2p): no collective call inside the loop, exact per-sweep early exit."""
         import torch.distributed as dist
         from rl_agents_b200.engine.vi import VIEngine
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.check_every = max(1, int(check_every))
+        self.exchange = exchange
+        self.max_iterations = int(max_iterations)
+        self.peer = None
         if tables_are_local:
             if n_states is None:
                 raise ValueError("tables_are_local needs n_states (the whole MDP's state count)")
@@ -92,11 +143,86 @@ class DistributedVI(object):
         self.n_states = S
         self.engine = VIEngine(mode, slab[0], slab[1], slab[2], nxt=slab[3], gamma=gamma, device=device,
                                row_begin=b, row_end=e, n_states=S, rtol=rtol, atol=atol)
+        if exchange == "p2p":
+            self._setup_p2p()
+        elif exchange != "nccl":
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+
+    # ------------------------------------------------------------------ fused exchange over peer memory
+    def _setup_p2p(self):
+        from rl_agents_b200 import _lib
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError("p2p exchange supports up to %d ranks" % _lib.MAX_PEERS)
+        S, G, T = self.n_states, self.world, self.max_iterations
+        al = lambda n: (n + 255) // 256 * 256
+        self._off_v = [0, al(S * 8)]
+        self._off_flags = self._off_v[1] + al(S * 8)
+        self._off_parts = self._off_flags + al(G * 4)
+        self._off_local = self._off_parts + al(T * G * 4)        # viol_local [T] + done [T]: never read by peers
+        self._bytes = self._off_local + al(T * 4) + al(T * 4)
+        self.peer = PeerBuffer(self._bytes, self.group)
+        x = _lib.VIP2P()
+        x.world, x.rank = G, self.rank
+        for r in range(G):
+            base = self.peer.ptrs[r]
+            x.v[0][r], x.v[1][r] = base + self._off_v[0], base + self._off_v[1]
+            x.flags[r], x.parts[r] = base + self._off_flags, base + self._off_parts
+        x.viol_local = self.peer.local + self._off_local
+        x.done = self.peer.local + self._off_local + al(T * 4)
+        self._x = x
+
+    def _solve_p2p(self, iterations):
+        import ctypes
+        import torch
+        from rl_agents_b200 import _lib
+        if iterations > self.max_iterations:
+            raise ValueError("iterations %d > max_iterations %d" % (iterations, self.max_iterations))
+        eng, lib = self.engine, self.peer.lib
+        stream = _lib.current_stream()
+        for q in eng.q:
+            q.zero_()
+        _lib.check(lib.b2_p2p_memset(ctypes.c_void_p(self.peer.local), 0, self._bytes, stream))
+        torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)      # every rank's flags are zero before anybody publishes
+        for k in range(iterations):
+            _lib.check(lib.b2_vi_sweep_p2p(eng.problem, self._x, _lib.ptr(eng.q[k & 1]), _lib.ptr(eng.q[(k + 1) & 1]),
+                                           k, stream))
+        parts = np.zeros((iterations, self.world), dtype=np.int32)
+        _lib.check(lib.b2_p2p_read(parts.ctypes.data_as(ctypes.c_void_p),
+                                   ctypes.c_void_p(self.peer.local + self._off_parts), parts.nbytes, stream))
+        # a rank reads its own table only after ITS last kernel retired; peers publish their last entry
+        # when THEIR last kernel retires: wait for everybody before trusting the last row
+        self.dist.barrier(group=self.group)
+        _lib.check(lib.b2_p2p_read(parts.ctypes.data_as(ctypes.c_void_p),
+                                   ctypes.c_void_p(self.peer.local + self._off_parts), parts.nbytes, stream))
+        viol = parts.sum(axis=1)
+        zero = np.nonzero(viol == 0)[0]
+        if zero.size:
+            k = int(zero[0])
+            return eng.q[k & 1], k + 1
+        return eng.q[iterations & 1], int(iterations)
+
+    def v_slab(self, iterations_done):
+        """(p2p) this rank's copy of the full V after `iterations_done` sweeps, as a host array."""
+        import ctypes
+        from rl_agents_b200 import _lib
+        out = np.zeros(self.n_states, dtype=np.float64)
+        _lib.check(self.peer.lib.b2_p2p_read(out.ctypes.data_as(ctypes.c_void_p),
+                                             ctypes.c_void_p(self.peer.local + self._off_v[iterations_done & 1]),
+                                             out.nbytes, _lib.current_stream()))
+        return out
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     def solve(self, iterations, exchange=True):
         """Returns (this rank's Q slab on device, sweeps).  No host sync inside the loop: the sweep kernels
         read the all-reduced violation counters from device memory.  exchange=False skips the collectives
         (timing of the compute alone; the values are then meaningless)."""
+        if self.exchange == "p2p" and exchange:
+            return self._solve_p2p(iterations)
         eng = self.engine
         eng.reset(iterations)
         m = self.check_every

@@ -46,6 +46,18 @@ def main():
     q3, sweeps3 = dvi3.solve(80)
     out["vi_check_every_ok"] = bool(np.allclose(q3.cpu().numpy(), q_ref[b:e], rtol=1e-4, atol=1e-7)) \
         and sweeps_ref <= sweeps3 <= sweeps_ref + 4
+    # --- exchange fused into the sweep kernel over peer memory (no NCCL in the loop): bit-exact, same sweep count ---
+    S2, A2, B2 = 4096, 8, 4
+    Pp, Np, Rp = oenvs.garnet(S2, A2, B2, seed=6)
+    termp = np.zeros(S2, bool)
+    termp[::97] = True
+    qp_ref, sweeps_p_ref = planners.value_iteration("sparse", Pp, Rp, termp, 0.7, 60, nxt=Np)
+    bp, ep = shard_range(S2, rank, world)
+    dvi4 = DistributedVI("sparse", Pp, Rp, termp, nxt=Np, gamma=0.7, device=dev, exchange="p2p", max_iterations=64)
+    for rep in range(2):                       # twice: the flags / counters are reset correctly between solves
+        q4, sweeps4 = dvi4.solve(60)
+        out["vi_p2p_ok_%d" % rep] = bool(np.array_equal(q4.cpu().numpy(), qp_ref[bp:ep])) and sweeps4 == sweeps_p_ref
+    dvi4.close()
     # --- root-parallel MCTS: one all-reduce of root statistics ---
     words = oenvs.make_highway_state(3).pack()
     ss = np.random.SeedSequence(11).spawn(world)[rank]
