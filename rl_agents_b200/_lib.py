@@ -40,7 +40,7 @@ MAX_PEERS = 8
 class VIP2P(ctypes.Structure):
     _fields_ = [("world", c_int32), ("rank", c_int32), ("v", (c_void_p * MAX_PEERS) * 2),
                 ("flags", c_void_p * MAX_PEERS), ("parts", c_void_p * MAX_PEERS),
-                ("viol_local", c_void_p), ("done", c_void_p)]
+                ("viol_local", c_void_p), ("done", c_void_p), ("status", c_void_p)]
 
 
 class OPDConfig(ctypes.Structure):

@@ -54,8 +54,12 @@ __global__ void __launch_bounds__(256) vi_sweep_row_p2p_kernel(P2PSweep g) {
     if (tid == 0) s_conv = 0;
     if (k > 0) {
         if (tid < world) {
+            // bounded: a peer that never arrives (crashed rank, mismatched launch) must not hang the GPU
             const int32_t* f = g.x.flags[rank] + tid;
-            while (ld_acquire_sys(f) < k) {}
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) < k) {
+                if (clock64() - t0 > 8000000000ll) { atomicExch(g.x.status, 1); break; }
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -206,7 +210,7 @@ extern "C" int b2_vi_sweep_p2p(const b2_vi_problem* p, const b2_vi_p2p* x, const
     B2_REQUIRE(sweep_index >= 0 && p->row_end > p->row_begin && p->row_end <= p->n_states, "bad shape");
     for (int r = 0; r < x->world; ++r)
         B2_REQUIRE(x->v[0][r] && x->v[1][r] && x->flags[r] && x->parts[r], "peer pointer missing");
-    B2_REQUIRE(x->viol_local && x->done, "scratch missing");
+    B2_REQUIRE(x->viol_local && x->done && x->status, "scratch missing");
     P2PSweep g;
     g.R = p->reward; g.term = p->terminal; g.q_old = q_old; g.q_new = q_new;
     g.rows = p->row_end - p->row_begin; g.row_begin = p->row_begin; g.A = p->n_actions; g.sweep = sweep_index;

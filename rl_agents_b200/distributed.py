@@ -159,7 +159,7 @@ class DistributedVI(object):
         self._off_flags = self._off_v[1] + al(S * 8)
         self._off_parts = self._off_flags + al(G * 4)
         self._off_local = self._off_parts + al(T * G * 4)        # viol_local [T] + done [T]: never read by peers
-        self._bytes = self._off_local + al(T * 4) + al(T * 4)
+        self._bytes = self._off_local + al(T * 4) + al(T * 4) + 256
         self.peer = PeerBuffer(self._bytes, self.group)
         x = _lib.VIP2P()
         x.world, x.rank = G, self.rank
@@ -169,6 +169,7 @@ class DistributedVI(object):
             x.flags[r], x.parts[r] = base + self._off_flags, base + self._off_parts
         x.viol_local = self.peer.local + self._off_local
         x.done = self.peer.local + self._off_local + al(T * 4)
+        x.status = self.peer.local + self._off_local + 2 * al(T * 4)
         self._x = x
 
     def _solve_p2p(self, iterations):
@@ -195,6 +196,10 @@ class DistributedVI(object):
         self.dist.barrier(group=self.group)
         _lib.check(lib.b2_p2p_read(parts.ctypes.data_as(ctypes.c_void_p),
                                    ctypes.c_void_p(self.peer.local + self._off_parts), parts.nbytes, stream))
+        status = np.zeros(1, dtype=np.int32)
+        _lib.check(lib.b2_p2p_read(status.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(self._x.status), 4, stream))
+        if int(status[0]) != 0:
+            raise _lib.B2Error("p2p value iteration: a peer's arrival flag timed out (rank %d)" % self.rank)
         viol = parts.sum(axis=1)
         zero = np.nonzero(viol == 0)[0]
         if zero.size:
