@@ -294,6 +294,44 @@ int b2_mcts_plan(const b2_mcts_config* cfg, const int32_t* root_states, const b2
                  uint64_t* rng, int8_t* plan, int32_t* result, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Wavefront MCTS: ONE decision searched by the whole GPU.  The reference's episode (selection mcts.py:141-149,
+ * expansion :151-154, rollout :160-177, backup :257-265, recommendation :212-218) run in waves of `width`
+ * episodes: selections in episode order with virtual counts, counter-based randomness, exact fixed-point
+ * value sums.  Bit-identical with the specification oracle/planners.py::mcts_plan_wavefront.
+ * ---------------------------------------------------------------------- */
+typedef struct b2_mcts_wave_config {
+    int32_t env_kind;
+    int32_t n_actions;
+    int32_t episodes;        /* config["episodes"]                              */
+    int32_t horizon;         /* config["horizon"] (<= 64)                       */
+    int32_t node_capacity;   /* >= 1 + episodes * n_actions (episode e owns ids 1 + e*n_actions ..) */
+    int32_t width;           /* episodes per wave, 1..1024                      */
+    int32_t rollout_policy;  /* 0 random_available (the only one implemented)   */
+    int32_t prior_policy;
+    double temperature;      /* config["temperature"] (:127)                    */
+    uint64_t seed;           /* counter-based generator seed                    */
+    const double* gamma_pow; /* [horizon+1] gamma**h                            */
+    b2_finite_mdp mdp;
+    int32_t max_ctas;        /* 0: one CTA per SM                               */
+    int32_t reserved;
+} b2_mcts_wave_config;
+
+typedef struct b2_mcts_wave_tree {   /* [node_capacity] each; unused ids keep parent == -2 */
+    int32_t* parent;
+    int32_t* first_child;
+    int32_t* count;
+    int32_t* meta;           /* action | n_children << 8                        */
+    int64_t* vsum;           /* sum of the returns backed up through the node, 2^-40 units */
+    double* value;           /* vsum * 2^-40 / count (written at the end)       */
+} b2_mcts_wave_tree;
+
+int64_t b2_mcts_wave_workspace_bytes(const b2_mcts_wave_config* cfg);
+/* root_state: [1] state id or [136] words; plan: int8 [horizon]; result: int32 [B2_MCTS_RESULT_WORDS]:
+ * [0] node_capacity [1] plan_len [2] env steps [3] waves [4..7] phase clocks.  Cooperative launch. */
+int b2_mcts_plan_wave(const b2_mcts_wave_config* cfg, const int32_t* root_state, const b2_mcts_wave_tree* tree,
+                      void* workspace, int8_t* plan, int32_t* result, void* stream);
+
+/* ------------------------------------------------------------------------
  * OLOP / KL-OLOP -- rl_agents/agents/tree_search/olop.py
  * ---------------------------------------------------------------------- */
 typedef struct b2_olop_config {

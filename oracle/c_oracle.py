@@ -27,6 +27,7 @@ def load():
         _lib.opd_highway_plan.restype = ctypes.c_int
         _lib.opd_highway_plan_wave.restype = ctypes.c_int
         _lib.mcts_highway_plan.restype = ctypes.c_int
+        _lib.mcts_highway_plan_wave.restype = ctypes.c_int
     return _lib
 
 
@@ -104,3 +105,21 @@ def mcts_plan(root_words, episodes, horizon, gamma, temperature, rng_words):
                               _p(i32["count"]), _p(i32["first_child"]), _p(i32["n_children"]), _p(f64["value"]),
                               _p(f64["prior"]))
     return {k: v[:n] for k, v in {**i32, **f64}.items()}, words
+
+
+def mcts_plan_wave(root_words, episodes, horizon, gamma, temperature, width, seed):
+    """The wavefront MCTS specification (oracle.planners.mcts_plan_wavefront) in C -> tree dict + env_steps."""
+    lib = load()
+    cap = 1 + int(episodes) * 5
+    i32 = {k: np.zeros(cap, dtype=np.int32) for k in ("parent", "action", "count", "first_child", "n_children")}
+    vsum = np.zeros(cap, dtype=np.int64)
+    value = np.zeros(cap, dtype=np.float64)
+    gp = np.array([float(gamma) ** h for h in range(int(horizon) + 1)], dtype=np.float64)
+    root = np.ascontiguousarray(root_words, dtype=np.int32)
+    steps = lib.mcts_highway_plan_wave(_p(root), ctypes.c_int(int(episodes)), ctypes.c_int(int(horizon)), _p(gp),
+                                       ctypes.c_double(temperature), ctypes.c_int(int(width)),
+                                       ctypes.c_uint64(int(seed) & ((1 << 64) - 1)), _p(i32["parent"]), _p(i32["action"]),
+                                       _p(i32["count"]), _p(i32["first_child"]), _p(i32["n_children"]), _p(vsum), _p(value))
+    out = dict(i32)
+    out["vsum"], out["value"], out["env_steps"] = vsum, value, steps
+    return out

@@ -126,7 +126,7 @@ def opd_plan_wavefront(env, budget, gamma, width, terminal_reward=0.0, np_random
     t.reward, t.lower, t.upper, t.done = [0.0], [0.0], [0.0], [False]
     t.parent, t.action, t.depth, t.count, t.first_child, t.n_children = [-1], [-1], [0], [1], [-1], [0]
     states = [env]
-    leaves = [0]
+    leaves = {0}                                     # the frontier; its order is given by the sort key below
     remaining = int(budget) // env.action_space.n
     t.waves, t.terminal_expansions = [], 0
     while remaining > 0:
@@ -154,7 +154,7 @@ def opd_plan_wavefront(env, budget, gamma, width, terminal_reward=0.0, np_random
                 t.first_child.append(-1); t.n_children.append(0)
                 t.reward.append(reward); t.lower.append(lo); t.upper.append(up); t.done.append(bool(done))
                 states.append(st)
-                leaves.append(c)
+                leaves.add(c)
             states[best] = None
         remaining -= k
     # counts (:64-65: +1 on self and every ancestor per created node) and backups (:74-79), bottom-up
@@ -320,6 +320,128 @@ def mcts_plan(env, episodes, horizon, gamma, temperature, np_random,
         kids = list(t.children(node))
         counts = np.array([t.count[c] for c in kids])
         ties = np.nonzero(counts == np.amax(counts))[0]
+        best = max(ties, key=lambda i: t.value[kids[i]])
+        plan.append(t.action[kids[best]])
+        node = kids[best]
+    return plan, t
+
+
+_M64 = (1 << 64) - 1
+
+
+def splitmix64(x):
+    """The counter-based generator of the wavefront planners (same 64-bit arithmetic in C and CUDA)."""
+    z = (x + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def wave_random(seed, episode, step, stream, n):
+    """Uniform integer in [0, n) for (episode, step, stream): stream 0 = selection tie-break, 1 = rollout."""
+    key = (seed + episode * 0x9E3779B97F4A7C15 + (step + 1) * 0xD1B54A32D192ED03 + stream * 0x8CB92BA72F3D8DD7) & _M64
+    return int((splitmix64(key) >> 33) % n)
+
+
+FIX_SCALE = float(1 << 40)
+
+
+def mcts_plan_wavefront(env, episodes, horizon, gamma, temperature, width, seed):
+    """SPECIFICATION of the device's wavefront MCTS (b2_mcts_plan_wave), not a reference algorithm.
+
+    The reference's MCTS.plan (mcts.py:179-184) runs its episodes one after the other; every episode reads
+    the statistics the previous one wrote and draws from one sequential PCG64 stream, so 4096 rollouts
+    cannot run in parallel.  The wavefront keeps the reference's episode (selection :141-149, expansion
+    :151-154, rollout :160-177, update_branch :257-265, recommendation :212-218) and changes three things:
+      * episodes run in waves of `width`; inside a wave the selections are made in episode order on the
+        statistics of the wave start plus VIRTUAL counts (an episode that passes through a child adds one
+        to that child's count for the later selections of the same wave), so a wave spreads over the tree
+        instead of repeating one path; a childless node reached by several episodes of a wave is expanded
+        once, by the first of them, and every one of them rolls out from it;
+      * randomness is counter based -- wave_random(seed, episode, step, stream) -- instead of a sequential
+        stream: tie-breaks of the selection (random_argmax, abstract.py:296-311) and rollout actions
+        (uniform over the available actions) do not depend on the execution order;
+      * a node's value is the mean of the returns backed up through it, accumulated as an exact 64-bit
+        fixed-point sum (2^-40 units), so the backup is order independent (the reference's incremental
+        mean :253 gives the same mean up to rounding).
+    Node ids: root 0; episode e owns the ids 1 + e * n_actions ... for the children it may create (unused
+    ids keep parent = -2).  Returns (plan, tree)."""
+    A = env.action_space.n
+    cap = 1 + episodes * A
+    t = Tree()
+    t.parent = [-2] * cap
+    t.action = [-1] * cap
+    t.count = [0] * cap
+    t.first_child = [-1] * cap
+    t.n_children = [0] * cap
+    t.vsum = [0] * cap
+    t.parent[0] = -1
+    t.env_steps = 0
+
+    def value(c):
+        return (float(t.vsum[c]) / FIX_SCALE) / t.count[c] if t.count[c] > 0 else 0.0
+
+    for w0 in range(0, episodes, width):
+        wave = range(w0, min(w0 + width, episodes))
+        virtual, expander, paths = {}, {}, {}
+        for e in wave:                                              # selections, episode order, virtual counts
+            node, depth, path = 0, 0, []
+            while depth < horizon and t.n_children[node] > 0:
+                kids = list(t.children(node))
+                n = len(kids)
+                prior = 1.0 / n
+                x = [value(c) + temperature * n * prior / (t.count[c] + virtual.get(c, 0) + 1) for c in kids]
+                best = max(x)
+                ties = [i for i in range(n) if x[i] == best]
+                child = kids[ties[wave_random(seed, e, depth, 0, len(ties))]]
+                virtual[child] = virtual.get(child, 0) + 1
+                path.append(child)
+                node = child
+                depth += 1
+            paths[e] = path
+            if depth < horizon and node not in expander:
+                expander[node] = e
+        results = {}
+        for e in wave:                                              # simulations: independent of each other
+            state = copy.deepcopy(env)
+            path, total, terminal, reached = paths[e], 0.0, False, 0
+            for h, c in enumerate(path):
+                _, reward, terminal, _, _ = state.step(t.action[c])
+                t.env_steps += 1
+                total += gamma ** h * reward
+                reached = h + 1
+                if terminal:
+                    break
+            if not terminal:
+                depth = len(path)
+                leaf = path[-1] if path else 0
+                if depth < horizon and expander.get(leaf) == e:
+                    actions = _available_actions(state)
+                    base = 1 + e * A
+                    t.first_child[leaf], t.n_children[leaf] = base, len(actions)
+                    for i, a in enumerate(actions):
+                        t.parent[base + i], t.action[base + i] = leaf, int(a)
+                for h in range(depth, horizon):
+                    actions = _available_actions(state)
+                    a = actions[wave_random(seed, e, h, 1, len(actions))]
+                    _, reward, term, trunc, _ = state.step(a)
+                    t.env_steps += 1
+                    total += gamma ** h * reward
+                    if term or trunc:
+                        break
+            results[e] = (reached, total)
+        for e in wave:                                              # backup: exact integer sums
+            reached, total = results[e]
+            fixed = int(np.rint(total * FIX_SCALE))
+            for c in [0] + paths[e][:reached]:
+                t.count[c] += 1
+                t.vsum[c] += fixed
+    t.value = [value(c) for c in range(cap)]
+    plan, node = [], 0
+    while t.n_children[node] > 0:
+        kids = list(t.children(node))
+        counts = [t.count[c] for c in kids]
+        ties = [i for i in range(len(kids)) if counts[i] == max(counts)]
         best = max(ties, key=lambda i: t.value[kids[i]])
         plan.append(t.action[kids[best]])
         node = kids[best]

@@ -76,6 +76,17 @@ class MCTSConfig(ctypes.Structure):
                 ("uniform_cdf", c_void_p), ("mdp", FiniteMDP), ("resume_nodes", c_void_p)]
 
 
+class MCTSWaveConfig(ctypes.Structure):
+    _fields_ = [("env_kind", c_int32), ("n_actions", c_int32), ("episodes", c_int32), ("horizon", c_int32),
+                ("node_capacity", c_int32), ("width", c_int32), ("rollout_policy", c_int32),
+                ("prior_policy", c_int32), ("temperature", c_double), ("seed", ctypes.c_uint64),
+                ("gamma_pow", c_void_p), ("mdp", FiniteMDP), ("max_ctas", c_int32), ("reserved", c_int32)]
+
+
+class MCTSWaveTree(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("parent", "first_child", "count", "meta", "vsum", "value")]
+
+
 class MCTSTree(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("parent", "first_child", "count", "meta", "value", "prior")]
 
@@ -119,6 +130,9 @@ EXPORTS = {
     "b2_opd_copy_tree": (c_int, [c_void_p, c_int32, c_int32] + [c_void_p] * 7),
     "b2_mcts_plan": (c_int, [ctypes.POINTER(MCTSConfig), c_void_p, ctypes.POINTER(MCTSTree), c_void_p, c_void_p,
                              c_void_p, c_void_p]),
+    "b2_mcts_wave_workspace_bytes": (c_int64, [ctypes.POINTER(MCTSWaveConfig)]),
+    "b2_mcts_plan_wave": (c_int, [ctypes.POINTER(MCTSWaveConfig), c_void_p, ctypes.POINTER(MCTSWaveTree), c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "b2_olop_plan": (c_int, [ctypes.POINTER(OLOPConfig), c_void_p, ctypes.POINTER(OLOPTree), c_void_p, c_void_p,
                              c_void_p, c_void_p]),
 }

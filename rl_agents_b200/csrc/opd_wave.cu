@@ -42,6 +42,13 @@ struct Control {                            // head of the workspace; zeroed by 
                          // 4 simulate (CTA 0's share), 5 barrier after simulate, 6 bottom-up + plan, 7 bisection steps
 };
 
+constexpr int MAX_STEPS = 80;
+struct DistScratch {                        // cross-CTA reductions of the distributed selection, by wave parity
+    unsigned long long gmin[2], gmax[2];
+    unsigned gt[2], pad[2];
+    unsigned counts[2][MAX_STEPS][4];
+};
+
 struct Args {
     b2_opd_wave_config cfg;
     b2_opd_tree tree;
@@ -51,6 +58,8 @@ struct Args {
     int32_t* exp_order;    // [n_expansions] expanded leaves, wave-major, id order inside a wave
     int32_t* wave_start;   // [n_expansions + 1]
     int32_t* work;         // [width * n_actions] leaf | action << 28 for every child of the current wave
+    DistScratch* dscr;     // distributed selection (trees larger than one shared-memory tile)
+    int2* cta_cnt;         // [grid] per-CTA (taken-by-threshold, equal-to-threshold) counts
     int8_t* plan;
     int32_t* result;
 };
@@ -123,6 +132,253 @@ __device__ __forceinline__ void block_scan2(int a, int b, SelShared& sh, int& ea
     ea = wa + ia - a;
     eb = wb + ib - b;
     __syncthreads();
+}
+
+// CTA 0: lay out the children of the k chosen leaves (exp_order[n_expanded .. n_expanded + k), id order):
+// child ids by prefix sum of the available-action counts, parent records, work list.
+__device__ int layout_wave(const Args& a, SelShared& sh, unsigned long long* skeys, bool resident, int n_nodes,
+                           int n_expanded, int k, int slot, long long* prof) {
+    const int tid = threadIdx.x;
+    long long t0 = clock64();
+    const int32_t* sel = a.exp_order + n_expanded;
+    // ---- children layout: ids by prefix sum of the available-action counts, in leaf-id order ----
+    int run = 0, term = 0;
+    for (int j0 = 0; j0 < k; j0 += THREADS) {
+        const int j = j0 + tid;
+        int leaf = 0, mask = 0, n = 0, meta = 0;
+        if (j < k) {
+            leaf = __ldcg(sel + j);
+            meta = __ldcg(a.tree.meta + leaf);
+            mask = a.cfg.env_kind == B2_ENV_HIGHWAY ? (meta >> 24) & 0x1f : (1 << a.cfg.n_actions) - 1;
+            n = __popc(mask);
+            term += (meta >> 16) & 1;
+        }
+        int en, e2, tn, t2;
+        block_scan2(n, 0, sh, en, e2, tn, t2);
+        if (j < k) {
+            const int c0 = n_nodes + run + en;
+            a.tree.first_child[leaf] = c0;
+            a.tree.meta[leaf] = meta | (n << 8);
+            a.keys[leaf] = -INFINITY;
+            if (resident) skeys[leaf] = ABSENT;
+            int q = 0;
+            for (int act_i = 0; act_i < MAX_BRANCH; ++act_i) {
+                int act;
+                if (a.cfg.env_kind == B2_ENV_HIGHWAY) {
+                    if (act_i >= 5) break;
+                    const int order[5] = {hw::A_IDLE, hw::A_LEFT, hw::A_RIGHT, hw::A_FASTER, hw::A_SLOWER};
+                    act = order[act_i];
+                } else {
+                    if (act_i >= a.cfg.n_actions) break;
+                    act = act_i;
+                }
+                if (mask & (1 << act)) {
+                    a.work[run + en + q] = leaf | (act << 28);
+                    ++q;
+                }
+            }
+        }
+        run += tn;
+    }
+    term = block_sum(term, sh.red, slot);
+    if (tid == 0) {
+        Control* c = a.ctl;
+        c->term_exp += term;
+        a.wave_start[c->n_waves] = n_expanded;
+        c->n_waves += 1;
+        a.wave_start[c->n_waves] = n_expanded + k;
+        c->wave_base = n_nodes;
+        c->wave_children = run;
+        c->n_nodes = n_nodes + run;
+        c->n_expanded = n_expanded + k;
+        prof[2] += clock64() - t0;
+    }
+    return run;
+}
+
+// ALL CTAs (trees that do not fit one shared-memory tile): the same selection with the key array split in
+// contiguous id slices, one per CTA; every reduction of the search (range, threshold counts, tie count,
+// compaction offsets) goes through global atomics + a grid barrier, so all CTAs take identical decisions.
+// Leaves the wave's k leaves in exp_order[n_expanded ..) in id order and returns k (0: search finished).
+__device__ int select_dist(const Args& a, SelShared& sh, unsigned long long* skeys, int n_nodes, int n_expanded,
+                           int wave, unsigned n_ctas) {
+    const int tid = threadIdx.x, bid = blockIdx.x;
+    const int remaining = a.cfg.n_expansions - n_expanded;
+    const int frontier = n_nodes - n_expanded;
+    const int k = min(min(a.cfg.width, remaining), frontier);
+    if (k <= 0) return 0;
+    const int par = wave & 1;
+    DistScratch* d = a.dscr;
+    volatile DistScratch* vd = a.dscr;
+    const int L = (n_nodes + (int)n_ctas - 1) / (int)n_ctas;
+    const int sb = min(bid * L, n_nodes), se = min(sb + L, n_nodes), len = se - sb;
+    const int n_tiles = (len + STAGE_CAP - 1) / STAGE_CAP;
+    auto stage = [&](int tile) {
+        const int base = sb + tile * STAGE_CAP, n = min(STAGE_CAP, se - base);
+        __syncthreads();
+#pragma unroll 8
+        for (int i = tid; i < n; i += THREADS) skeys[i] = sortable(__ldcg(a.keys + base + i));
+        __syncthreads();
+        return n;
+    };
+    auto chunk_of = [&](int n, int& lo, int& hi) {
+        const int c = ((n + THREADS - 1) / THREADS) | 1;
+        lo = min(tid * c, n);
+        hi = min(lo + c, n);
+    };
+    // the other parity's scratch is idle: reset it for the next wave
+    if (bid == 0) {
+        if (tid == 0) { d->gmin[par ^ 1] = ~0ull; d->gmax[par ^ 1] = 0ull; d->gt[par ^ 1] = 0u; }
+        for (int i = tid; i < MAX_STEPS * 4; i += THREADS) (&d->counts[par ^ 1][0][0])[i] = 0u;
+    }
+    int n0 = n_tiles > 0 ? stage(0) : 0;
+    int slot = 0;
+    // ---- range of the frontier keys ----
+    {
+        unsigned long long mx = 0, mn = ~0ull;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int n = t == 0 ? n0 : stage(t);
+            int b, e;
+            chunk_of(n, b, e);
+#pragma unroll 8
+            for (int i = b; i < e; ++i) {
+                const unsigned long long u = skeys[i];
+                if (u > ABSENT) { mx = max(mx, u); mn = min(mn, u); }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if ((tid & 31) == 0 && mx > ABSENT) { atomicMax(&d->gmax[par], mx); atomicMin(&d->gmin[par], mn); }
+    }
+    grid_barrier(a.ctl, n_ctas);
+    unsigned long long lo = vd->gmin[par], hi = vd->gmax[par], theta = 0;
+    bool exact = false;
+    if (k == frontier) { theta = lo; exact = true; }
+    int step = 0;
+    while (!exact) {
+        if (lo == hi) { theta = lo; break; }
+        const unsigned long long range = hi - lo, fifth = range / 5;
+        unsigned long long m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = range >= 5 ? lo + fifth * (j + 1) : min(lo + (unsigned long long)(j + 1), hi);
+        int c[4] = {0, 0, 0, 0};
+        for (int t = 0; t < n_tiles; ++t) {
+            const int n = n_tiles == 1 ? n0 : stage(t);
+            int b, e;
+            chunk_of(n, b, e);
+            int c01 = 0, c23 = 0;
+#pragma unroll 8
+            for (int i = b; i < e; ++i) {
+                const unsigned long long u = skeys[i];
+                c01 += (u >= m[0] ? 1 : 0) + (u >= m[1] ? 0x10000 : 0);
+                c23 += (u >= m[2] ? 1 : 0) + (u >= m[3] ? 0x10000 : 0);
+            }
+            const int w01 = __reduce_add_sync(0xffffffffu, c01), w23 = __reduce_add_sync(0xffffffffu, c23);
+            if ((tid & 31) == 0) { sh.red[slot * 2 * WARPS + (tid >> 5)] = w01; sh.red[slot * 2 * WARPS + WARPS + (tid >> 5)] = w23; }
+            __syncthreads();
+            int s01 = 0, s23 = 0;
+#pragma unroll
+            for (int i = 0; i < WARPS; ++i) { s01 += sh.red[slot * 2 * WARPS + i]; s23 += sh.red[slot * 2 * WARPS + WARPS + i]; }
+            slot ^= 1;
+            c[0] += s01 & 0xffff; c[1] += (unsigned)s01 >> 16; c[2] += s23 & 0xffff; c[3] += (unsigned)s23 >> 16;
+        }
+        if (tid < 4 && c[tid] != 0) atomicAdd(&d->counts[par][step][tid], (unsigned)c[tid]);
+        grid_barrier(a.ctl, n_ctas);
+        int j_gt = -1;
+        bool hit = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cj = (int)vd->counts[par][step][j];
+            if (cj == k && !hit) { theta = m[j]; hit = true; }
+            if (cj > k) j_gt = j;
+        }
+        ++step;
+        if (hit) { exact = true; break; }
+        const unsigned long long new_hi = j_gt < 3 ? m[j_gt + 1] - 1 : hi;
+        if (j_gt >= 0) lo = m[j_gt];
+        hi = new_hi;
+    }
+    int need_eq = 0;
+    if (!exact) {
+        int c = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int n = n_tiles == 1 ? n0 : stage(t);
+            int b, e;
+            chunk_of(n, b, e);
+#pragma unroll 8
+            for (int i = b; i < e; ++i) c += skeys[i] > theta ? 1 : 0;
+        }
+        c = block_sum(c, sh.red, slot);
+        slot ^= 1;
+        if (tid == 0 && c) atomicAdd(&d->gt[par], (unsigned)c);
+        grid_barrier(a.ctl, n_ctas);
+        need_eq = k - (int)vd->gt[par];
+    }
+    // ---- compaction, pass 1: this CTA's totals ----
+    {
+        int cg = 0, ce = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int n = n_tiles == 1 ? n0 : stage(t);
+            int b, e;
+            chunk_of(n, b, e);
+#pragma unroll 8
+            for (int i = b; i < e; ++i) {
+                const unsigned long long u = skeys[i];
+                if (exact) cg += u >= theta ? 1 : 0;
+                else { cg += u > theta ? 1 : 0; ce += u == theta ? 1 : 0; }
+            }
+        }
+        int eg, ee, tg, te;
+        block_scan2(cg, ce, sh, eg, ee, tg, te);
+        if (tid == 0) a.cta_cnt[bid] = make_int2(tg, te);
+    }
+    grid_barrier(a.ctl, n_ctas);
+    // ---- pass 2: offsets of the CTAs before this one, then ordered writes ----
+    int gt_before, eq_before;
+    {
+        int pg = 0, pe = 0;
+        if (tid < bid) {
+            const int2 v = __ldcg(a.cta_cnt + tid);
+            pg = v.x; pe = v.y;
+        }
+        int eg, ee;
+        block_scan2(pg, pe, sh, eg, ee, gt_before, eq_before);
+    }
+    int32_t* sel = a.exp_order + n_expanded;
+    int run_sel = gt_before + min(eq_before, need_eq), run_eq = eq_before;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int n = n_tiles == 1 ? n0 : stage(t);
+        const int base = sb + t * STAGE_CAP;
+        int b, e;
+        chunk_of(n, b, e);
+        int cg = 0, ce = 0;
+#pragma unroll 8
+        for (int i = b; i < e; ++i) {
+            const unsigned long long u = skeys[i];
+            if (exact) cg += u >= theta ? 1 : 0;
+            else { cg += u > theta ? 1 : 0; ce += u == theta ? 1 : 0; }
+        }
+        int eg, ee, tg, te;
+        block_scan2(cg, ce, sh, eg, ee, tg, te);
+        int eq_seen = run_eq + ee;
+        int pos = run_sel + eg + min(eq_seen, need_eq) - min(run_eq, need_eq);
+        for (int i = b; i < e; ++i) {
+            const unsigned long long u = skeys[i];
+            bool take;
+            if (exact) take = u >= theta;
+            else if (u > theta) take = true;
+            else if (u == theta) { take = eq_seen < need_eq; ++eq_seen; }
+            else take = false;
+            if (take) sel[pos++] = base + i;
+        }
+        run_sel += tg + min(run_eq + te, need_eq) - min(run_eq, need_eq);
+        run_eq += te;
+    }
+    grid_barrier(a.ctl, n_ctas);
+    return k;
 }
 
 // CTA 0: choose this wave's leaves and lay out their children.  Returns the number of children (0: done).
@@ -285,59 +541,8 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
         run_eq += te;
     }
     __syncthreads();
-    // ---- children layout: ids by prefix sum of the available-action counts, in leaf-id order ----
-    int run = 0, term = 0;
-    for (int j0 = 0; j0 < k; j0 += THREADS) {
-        const int j = j0 + tid;
-        int leaf = 0, mask = 0, n = 0, meta = 0;
-        if (j < k) {
-            leaf = sel[j];
-            meta = __ldcg(a.tree.meta + leaf);
-            mask = a.cfg.env_kind == B2_ENV_HIGHWAY ? (meta >> 24) & 0x1f : (1 << a.cfg.n_actions) - 1;
-            n = __popc(mask);
-            term += (meta >> 16) & 1;
-        }
-        int en, e2, tn, t2;
-        block_scan2(n, 0, sh, en, e2, tn, t2);
-        if (j < k) {
-            const int c0 = n_nodes + run + en;
-            a.tree.first_child[leaf] = c0;
-            a.tree.meta[leaf] = meta | (n << 8);
-            a.keys[leaf] = -INFINITY;
-            if (resident) skeys[leaf] = ABSENT;
-            int q = 0;
-            for (int act_i = 0; act_i < MAX_BRANCH; ++act_i) {
-                int act;
-                if (a.cfg.env_kind == B2_ENV_HIGHWAY) {
-                    if (act_i >= 5) break;
-                    const int order[5] = {hw::A_IDLE, hw::A_LEFT, hw::A_RIGHT, hw::A_FASTER, hw::A_SLOWER};
-                    act = order[act_i];
-                } else {
-                    if (act_i >= a.cfg.n_actions) break;
-                    act = act_i;
-                }
-                if (mask & (1 << act)) {
-                    a.work[run + en + q] = leaf | (act << 28);
-                    ++q;
-                }
-            }
-        }
-        run += tn;
-    }
-    term = block_sum(term, sh.red, slot);
-    if (tid == 0) {
-        Control* c = a.ctl;
-        c->term_exp += term;
-        a.wave_start[c->n_waves] = n_expanded;
-        c->n_waves += 1;
-        a.wave_start[c->n_waves] = n_expanded + k;
-        c->wave_base = n_nodes;
-        c->wave_children = run;
-        c->n_nodes = n_nodes + run;
-        c->n_expanded = n_expanded + k;
-        prof[2] += clock64() - t0;
-    }
-    return run;
+    if (tid == 0) prof[2] += clock64() - t0;
+    return layout_wave(a, sh, skeys, resident, n_nodes, n_expanded, k, slot, prof);
 }
 
 // node record of a new child: DeterministicNode.__init__ / update (deterministic.py:10-19, 45-63)
@@ -404,13 +609,35 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
         }
         __syncthreads();
     }
+    const bool dist_mode = a.cfg.node_capacity > STAGE_CAP;
+    if (dist_mode) {
+        if (blockIdx.x == 0 && tid == 0) {
+            a.dscr->gmin[0] = a.dscr->gmin[1] = ~0ull;
+            ctl->n_nodes = 1;
+        }
+        grid_barrier(ctl, n_ctas);
+    }
+    int wave = 0;
     long long tp = clock64();
     auto lap = [&](int slot) {
         if (blockIdx.x == 0 && tid == 0) { const long long t1 = clock64(); ctl->prof[slot] += t1 - tp; tp = t1; }
     };
     // ------------------------------------------------------------------ waves
     while (true) {
-        if (blockIdx.x == 0) {
+        if (dist_mode) {
+            const int nn = *(volatile int*)&ctl->n_nodes, ne = *(volatile int*)&ctl->n_expanded;
+            const int k = select_dist(a, sh, skeys, nn, ne, wave, n_ctas);
+            lap(1);
+            if (blockIdx.x == 0) {
+                int children = 0;
+                if (k > 0) children = layout_wave(a, sh, skeys, false, nn, ne, k, 0, ctl->prof);
+                if (tid == 0) {
+                    if (children == 0) ctl->stop = 1;
+                    tp = clock64();
+                }
+            }
+            ++wave;
+        } else if (blockIdx.x == 0) {
             const int nn = s_nodes, ne = s_expanded, ns = s_staged;
             __syncthreads();
             const int children = select_wave(a, sh, skeys, nn, ne, ns, ctl->prof);
@@ -522,7 +749,7 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
 static int64_t align_up(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 struct Layout {
-    int64_t ctl, keys, exp_order, wave_start, work, total;
+    int64_t ctl, keys, exp_order, wave_start, work, dscr, cta_cnt, total;
 };
 
 static Layout make_layout(const b2_opd_wave_config* c) {
@@ -532,7 +759,9 @@ static Layout make_layout(const b2_opd_wave_config* c) {
     l.exp_order = l.keys + align_up((int64_t)c->node_capacity * 8);
     l.wave_start = l.exp_order + align_up((int64_t)c->n_expansions * 4 + 4);
     l.work = l.wave_start + align_up(((int64_t)c->n_expansions + 2) * 4);
-    l.total = l.work + align_up((int64_t)c->width * c->n_actions * 4 + 4);
+    l.dscr = l.work + align_up((int64_t)c->width * c->n_actions * 4 + 4);
+    l.cta_cnt = l.dscr + align_up(sizeof(DistScratch));
+    l.total = l.cta_cnt + align_up(1024 * sizeof(int2));
     return l;
 }
 
@@ -574,8 +803,11 @@ extern "C" int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* ro
     a.exp_order = (int32_t*)(ws + l.exp_order);
     a.wave_start = (int32_t*)(ws + l.wave_start);
     a.work = (int32_t*)(ws + l.work);
+    a.dscr = (wave::DistScratch*)(ws + l.dscr);
+    a.cta_cnt = (int2*)(ws + l.cta_cnt);
     a.plan = plan; a.result = result;
     B2_CUDA_CHECK(cudaMemsetAsync(a.ctl, 0, sizeof(wave::Control), stream));
+    B2_CUDA_CHECK(cudaMemsetAsync(a.dscr, 0, sizeof(wave::DistScratch), stream));
     const int stage = cfg->node_capacity < wave::STAGE_CAP ? cfg->node_capacity : wave::STAGE_CAP;
     const size_t smem = (size_t)stage * 8;
     B2_CUDA_CHECK(cudaFuncSetAttribute(wave::opd_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -585,6 +817,7 @@ extern "C" int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* ro
     // one CTA per SM; a wave of w children keeps ceil(w / 16) CTAs busy, the others only pass the barriers
     int grid = sm_count();
     if (cfg->max_ctas > 0 && cfg->max_ctas < grid) grid = cfg->max_ctas;
+    if (grid > wave::THREADS) grid = wave::THREADS;      // the distributed selection scans the CTA table with one block
     void* params[] = {&a};
     B2_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)wave::opd_wave_kernel, dim3(grid), dim3(wave::THREADS), params,
                                               smem, stream));

@@ -138,3 +138,66 @@ class MCTSEngine(object):
                 "count": self.count[tree, :n].cpu().numpy(), "value": self.value[tree, :n].cpu().numpy(),
                 "prior": self.prior[tree, :n].cpu().numpy(),
                 "first_child": self.first_child[tree, :n].cpu().numpy(), "n_children": (meta >> 8) & 0xff}
+
+
+class MCTSWaveEngine(object):
+    """ONE MCTS decision searched by the whole GPU in waves of `width` episodes (b2_mcts_plan_wave);
+    bit-identical with the specification oracle/planners.py::mcts_plan_wavefront."""
+
+    def __init__(self, env_kind, n_actions, episodes, horizon, gamma, temperature, width, mdp=None, device="cuda",
+                 max_ctas=0):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.n_actions, self.episodes, self.horizon = int(n_actions), int(episodes), int(horizon)
+        self.width = max(1, min(int(width), 1024))
+        self.capacity = 1 + self.episodes * self.n_actions
+        gp, _ = gamma_tables(gamma, self.horizon + 1)
+        self.gamma_pow = torch.as_tensor(gp, device=self.device)
+        self.tables = FiniteTables(mdp, self.device) if env_kind == _lib.ENV_FINITE else None
+        i32 = torch.int32
+        self.parent = torch.empty(self.capacity, dtype=i32, device=self.device)
+        self.first_child = torch.empty(self.capacity, dtype=i32, device=self.device)
+        self.count = torch.empty(self.capacity, dtype=i32, device=self.device)
+        self.meta = torch.empty(self.capacity, dtype=i32, device=self.device)
+        self.vsum = torch.empty(self.capacity, dtype=torch.int64, device=self.device)
+        self.value = torch.empty(self.capacity, dtype=torch.float64, device=self.device)
+        self.cfg = _lib.MCTSWaveConfig(env_kind, self.n_actions, self.episodes, self.horizon, self.capacity, self.width,
+                                       0, 0, float(temperature), 0, self.gamma_pow.data_ptr(),
+                                       self.tables.struct() if self.tables else _lib.FiniteMDP(), int(max_ctas), 0)
+        self.tree = _lib.MCTSWaveTree(*[t.data_ptr() for t in (self.parent, self.first_child, self.count, self.meta,
+                                                               self.vsum, self.value)])
+        ws = self.lib.b2_mcts_wave_workspace_bytes(self.cfg)
+        if ws < 0:
+            raise _lib.B2Error("unsupported wavefront MCTS configuration")
+        self.workspace = torch.empty(int(ws), dtype=torch.uint8, device=self.device)
+        self.plan_buf = torch.empty(max(self.horizon, 1), dtype=torch.int8, device=self.device)
+        self.result = torch.empty(_lib.MCTS_RESULT_WORDS, dtype=i32, device=self.device)
+
+    def plan(self, root_state, seed):
+        """root_state: int32 device tensor [1] (finite) or [136]; seed: the counter-based generator's seed."""
+        assert root_state.dtype == self.torch.int32 and root_state.is_cuda and root_state.is_contiguous()
+        self.cfg.seed = int(seed) & ((1 << 64) - 1)
+        _lib.check(self.lib.b2_mcts_plan_wave(self.cfg, _lib.ptr(root_state), self.tree, _lib.ptr(self.workspace),
+                                              _lib.ptr(self.plan_buf), _lib.ptr(self.result), _lib.current_stream()))
+
+    def finish(self):
+        res = self.result.cpu().numpy()
+        return self.plan_buf.cpu().numpy()[:res[1]].astype(int).tolist(), res
+
+    def tree_dict(self):
+        meta = self.meta.cpu().numpy()
+        action = (meta & 0xff).astype(int)
+        action[action == 0xff] = -1
+        return {"parent": self.parent.cpu().numpy(), "action": action, "count": self.count.cpu().numpy(),
+                "first_child": self.first_child.cpu().numpy(), "n_children": (meta >> 8) & 0xff,
+                "vsum": self.vsum.cpu().numpy(), "value": self.value.cpu().numpy()}
+
+    def root_statistics(self):
+        d = self.tree_dict()
+        fc, n = int(d["first_child"][0]), int(d["n_children"][0])
+        counts, values = np.zeros(self.n_actions), np.zeros(self.n_actions)
+        for c in range(fc, fc + n):
+            counts[d["action"][c]], values[d["action"][c]] = d["count"][c], d["value"][c]
+        return counts, values

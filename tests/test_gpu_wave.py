@@ -185,3 +185,22 @@ def test_agent_wavefront_option_matches_the_specification_and_reuses_tables():
     agent.seed(0)
     plan, _ = planners.opd_plan_wavefront(oenvs.HighwayLite(seed=4), 400, 0.8, 32, np_random=np_random(0))
     assert agent.plan(henv.observation()) == plan
+
+
+def test_wave_finite_large_tree_distributed_selection_with_ties():
+    """A tree larger than one shared-memory tile: the selection runs on all CTAs (id slices, global
+    reductions); many exact ties at the threshold must still resolve to the lowest node ids."""
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    from rl_agents_b200.envs.finite_mdp import FiniteMDP
+    rng = np.random.default_rng(5)
+    T = rng.integers(0, 40, size=(40, 4)).astype(np.int32)
+    R = rng.choice([0.25, 0.5, 1.0], size=(40, 4))
+    term = np.zeros(40, bool)
+    for width in (700, 4096):
+        eng = OPDWaveEngine(_lib.ENV_FINITE, 4, 120000, 0.9, width, mdp=FiniteMDP("deterministic", T, R, term))
+        eng.plan(torch.tensor([0], dtype=torch.int32, device="cuda"))
+        plan, tree = planners.opd_plan_wavefront(oenvs.FiniteMDPLite(T, R, term), 120000, 0.9, width, np_random=np_random(0))
+        res = check(eng, plan, tree)
+        assert int(res[0, 7]) == len(tree.waves)
