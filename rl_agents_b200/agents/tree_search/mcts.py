@@ -82,6 +82,28 @@ class MCTS(AbstractPlanner):
         d = describe(state)
         replicas = int(self.config.get("root_parallel", 1) or 1)
         root = torch.from_numpy(d.root.reshape(1, -1) if d.root.size > 1 else d.root)
+        width = int(self.config.get("wavefront", 0) or 0)
+        if width > 0:
+            # extension ("wavefront": W): the ONE decision searched by the whole GPU in waves of W episodes
+            # (b2_mcts_plan_wave; specification oracle/planners.py::mcts_plan_wavefront).  The counter-based
+            # generator is seeded from the planner's stream, so agent.seed() still fixes the result.
+            from rl_agents_b200.engine.mcts import MCTSWaveEngine
+            if self.rollout_policy != "random_available" or self.prior_policy != "random_available":
+                raise NotImplementedError("wavefront MCTS implements the random_available policies")
+            key = ("wave", d.kind, d.n_actions, self.config["episodes"], self.config["horizon"], self.config["gamma"],
+                   self.config["temperature"], width, mdp_fingerprint(d.mdp))
+            if key != self._engine_key:
+                self.engine = MCTSWaveEngine(d.kind, d.n_actions, self.config["episodes"], self.config["horizon"],
+                                             self.config["gamma"], self.config["temperature"], width, mdp=d.mdp)
+                self._engine_key = key
+            eng = self.engine
+            seed = int(self.np_random.integers(0, 2 ** 63 - 1))
+            eng.plan(root.reshape(-1).to(eng.device).contiguous(), seed)
+            plan, _ = eng.finish()
+            self.last_tree = eng
+            counts, values = eng.root_statistics()
+            self.root_statistics = {"counts": counts, "values": values}
+            return plan
         if replicas <= 1:
             # the reference's semantics: one tree, strict episode order, the planner's own RNG stream
             eng = self._engine_for(d, 1, self.config["episodes"])

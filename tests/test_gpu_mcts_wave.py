@@ -82,3 +82,17 @@ def test_mcts_wave_highway_c3_full_size_vs_c_specification(width):
         used = c["parent"] != -2
         assert np.array_equal(d["action"][used], c["action"][used])
         assert int(res[2]) == c["env_steps"] and d["count"][0] == 4096
+
+
+def test_mcts_agent_wavefront_option():
+    """`"wavefront": W` in the MCTSAgent config: same plan as the specification seeded from the planner RNG."""
+    from rl_agents_b200.agents.tree_search.mcts import MCTSAgent
+    from rl_agents_b200.envs import HighwayLiteEnv
+    env = HighwayLiteEnv(seed=2)
+    agent = MCTSAgent(env, {"episodes": 96, "horizon": 6, "gamma": 0.8, "wavefront": 32})
+    agent.seed(5)
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(5)))
+    seed = int(rng.integers(0, 2 ** 63 - 1))
+    plan, _ = planners.mcts_plan_wavefront(oenvs.HighwayLite(seed=2), 96, 6, 0.8, 10.0, 32, seed)
+    assert agent.plan(env.observation()) == plan
+    assert agent.planner.root_statistics["counts"].sum() == 96 - 32      # the first wave only expands the root
