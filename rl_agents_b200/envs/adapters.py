@@ -20,13 +20,19 @@ def describe(env):
         d.kind, d.mdp = _lib.ENV_HIGHWAY, None
         d.root = np.ascontiguousarray(u.words, dtype=np.int32)
         return d
+    from rl_agents_b200.envs.highway_adapter import looks_like_highway_env, scene_from_highway_env
+    if kind is None and looks_like_highway_env(u):
+        # a live `highway_env` highway-v0 object: pack its scene; the search runs on the HighwayLite model of it
+        d.kind, d.mdp = _lib.ENV_HIGHWAY, None
+        d.root = scene_from_highway_env(u)
+        return d
     mdp = getattr(u, "mdp", None)
     if mdp is not None and hasattr(mdp, "transition") and hasattr(mdp, "reward"):
         # rl_agents_b200.envs.FiniteMDPEnv or the `finite_mdp` package's FiniteMDPEnv
         d.kind, d.mdp = _lib.ENV_FINITE, mdp
         d.root = np.array([int(mdp.state)], dtype=np.int32)
         return d
-    raise TypeError("rl_agents_b200 planners need a HighwayLiteEnv or a finite-MDP env "
+    raise TypeError("rl_agents_b200 planners need a HighwayLiteEnv, a highway_env highway-v0 env or a finite-MDP env "
                     "(got %r); see INTEGRATION.md for the env hand-off" % type(u).__name__)
 
 

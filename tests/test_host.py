@@ -208,3 +208,62 @@ def test_preprocess_env_applies_methods_in_sequence():
     out = preprocess_env(E(), [{"method": "simplify"}, {"method": "change", "args": 3}, {"method": "missing"}, {"args": 1}])
     assert out.tag == "sc3"
     assert _apply(E("x"), {"method": "nope"}).tag == "x"
+
+
+def _fake_highway_env(n_others=20, crashed_slot=None):
+    """An object with the attribute names of upstream highway-env's HighwayEnv (the package itself is absent)."""
+    class V(object):
+        pass
+
+    class Road(object):
+        pass
+
+    class Env(object):
+        unwrapped = property(lambda self: self)
+    rng = np.random.default_rng(1)
+    env, road = Env(), Road()
+    ego = V()
+    ego.position, ego.heading, ego.speed, ego.crashed = np.array([103.5, 8.0]), 0.01, 25.0, False
+    ego.lane_index, ego.target_lane_index = ("0", "1", 2), ("0", "1", 1)
+    ego.target_speeds, ego.speed_index, ego.target_speed = np.array([20.0, 25.0, 30.0]), 1, 25.0
+    vehicles = [ego]
+    for k in range(n_others):
+        v = V()
+        lane = int(rng.integers(0, 4))
+        v.position = np.array([103.5 + (k + 1) * 11.0 * (-1) ** k, 4.0 * lane])
+        v.heading, v.speed, v.crashed = 0.0, 21.0 + k * 0.1, k == crashed_slot
+        v.lane_index = v.target_lane_index = ("0", "1", lane)
+        v.target_speed, v.timer = 22.0, 0.25
+        vehicles.append(v)
+    road.vehicles = vehicles[1:4] + [ego] + vehicles[4:]          # the ego is not first in the upstream list either
+    env.road, env.vehicle = road, ego
+    env.config = {"lanes_count": 4, "duration": 40, "policy_frequency": 1, "action": {"type": "DiscreteMetaAction"}}
+    env.steps = 7
+
+    class Space(object):
+        n = 5
+    env.action_space = Space()
+    return env, vehicles
+
+
+def test_live_highway_env_object_is_packed_into_a_highway_lite_scene():
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.envs.adapters import describe
+    env, vehicles = _fake_highway_env(n_others=20, crashed_slot=2)
+    d = describe(env)
+    assert d.kind == _lib.ENV_HIGHWAY and d.n_actions == 5 and d.root.shape == (136,) and d.root.dtype == np.int32
+    f = d.root[:96].view(np.float32)
+    # slot 0 is the ego; the 15 nearest others follow by |dx|
+    assert f[0] == np.float32(103.5) and f[16] == np.float32(8.0) and f[32] == np.float32(0.01) and f[48] == 25.0
+    assert d.root[96] == 1 and d.root[129] == 1 and d.root[128] == 7          # target lane, speed index, step
+    order = sorted(vehicles[1:], key=lambda v: abs(v.position[0] - 103.5))[:15]
+    assert [float(x) for x in f[1:16]] == [float(np.float32(v.position[0])) for v in order]
+    assert [int(x) for x in d.root[112:128]] == [1] + [3 if v.crashed else 1 for v in order]
+    assert all(np.float32(v.timer) == f[80 + 1 + i] for i, v in enumerate(order))
+    # a scene with fewer vehicles leaves the remaining slots absent
+    env2, _ = _fake_highway_env(n_others=6)
+    assert describe(env2).root[112:128].tolist() == [1] * 7 + [0] * 9
+    # unsupported variants are refused loudly, not approximated silently
+    env2.config["lanes_count"] = 3
+    with pytest.raises(TypeError):
+        describe(env2)
