@@ -260,13 +260,20 @@ typedef struct b2_mcts_config {
     int32_t episodes;        /* config["episodes"] (:180)                    */
     int32_t horizon;         /* config["horizon"]                            */
     int32_t node_capacity;   /* per tree, >= 1 + episodes * n_actions        */
-    int32_t rollout_policy;  /* 0 random_available, 1 random (:46-72)        */
+    int32_t rollout_policy;  /* 0 random_available, 1 random, 2 preference (:46-97) */
     int32_t prior_policy;    /* idem, for expansion priors                   */
     double temperature;      /* config["temperature"] (:127)                 */
     const double* gamma_pow; /* [horizon+1] gamma**d                         */
     const double* uniform_cdf; /* [(n_actions+1), n_actions]: row n = cumsum(ones(n)/n)/last,
                                   the cdf Generator.choice(a, 1, p) searches (host numpy)  */
     b2_finite_mdp mdp;
+    /* "preference" policies (mcts.py:76-97): the preferred action label and, for n available actions with the
+     * preferred one at position k-1 of the env's action order (k = 0: not available -> uniform), row
+     * [(n * (n_actions+1) + k) * n_actions ..] of a host-made table: probabilities (prior policy) / the cdf
+     * Generator.choice searches (rollout policy).  Only read when the policy is 2. */
+    int32_t prior_pref_action, rollout_pref_action;
+    const double* pref_prior;    /* [(n_actions+1), (n_actions+1), n_actions] */
+    const double* pref_cdf;      /* [(n_actions+1), (n_actions+1), n_actions] */
     const int32_t* resume_nodes; /* nullable [n_trees]: > 0 -> the tree arrays already hold that many nodes
                                     (a re-rooted sub-tree, step_strategy "subtree", abstract.py:195-206,
                                     mcts.py:129-130) and the search continues from them; the caller sizes

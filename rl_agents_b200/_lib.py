@@ -73,7 +73,9 @@ class MCTSConfig(ctypes.Structure):
     _fields_ = [("env_kind", c_int32), ("n_trees", c_int32), ("n_actions", c_int32), ("episodes", c_int32),
                 ("horizon", c_int32), ("node_capacity", c_int32), ("rollout_policy", c_int32),
                 ("prior_policy", c_int32), ("temperature", c_double), ("gamma_pow", c_void_p),
-                ("uniform_cdf", c_void_p), ("mdp", FiniteMDP), ("resume_nodes", c_void_p)]
+                ("uniform_cdf", c_void_p), ("mdp", FiniteMDP), ("prior_pref_action", c_int32),
+                ("rollout_pref_action", c_int32), ("pref_prior", c_void_p), ("pref_cdf", c_void_p),
+                ("resume_nodes", c_void_p)]
 
 
 class MCTSWaveConfig(ctypes.Structure):

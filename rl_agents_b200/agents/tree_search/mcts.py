@@ -32,8 +32,11 @@ class MCTS(AbstractPlanner):
         self.rollout_policy = rollout_policy
         if not self.config["horizon"]:                                   # mcts.py:116-118
             self.config["episodes"], self.config["horizon"] = allocation(self.config["budget"], self.config["gamma"])
-        if self.config.get("closed_loop"):
-            raise NotImplementedError("closed_loop MCTS is outside the device planner's scope (DESIGN.md)")
+        # closed_loop (mcts.py:125,147,267-273) keys an extra node level on str(observation).  Both device env
+        # models are deterministic: every action node then has exactly one observation child carrying the same
+        # statistics, so visit counts, values and the recommended action equal the open-loop search's
+        # (golden: tests/golden "mcts_closed_loop", produced by the reference with closed_loop=True).  The
+        # reference's get_plan interleaves the observation keys with the actions; here the plan lists actions.
 
     @classmethod
     def default_config(cls):
@@ -44,7 +47,7 @@ class MCTS(AbstractPlanner):
     def _engine_for(self, d, replicas, episodes):
         from rl_agents_b200.engine.mcts import MCTSEngine
         key = (d.kind, d.n_actions, replicas, episodes, self.config["horizon"], self.config["gamma"],
-               self.config["temperature"], mdp_fingerprint(d.mdp))
+               self.config["temperature"], repr(self.rollout_policy), repr(self.prior_policy), mdp_fingerprint(d.mdp))
         if key != self._engine_key:
             # "subtree" keeps nodes alive for up to `horizon` decisions (a node at depth d survives d re-rootings)
             capacity = None
@@ -167,6 +170,6 @@ class MCTSAgent(AbstractTreeSearchAgent):
         kind = policy_config["type"]
         if kind in ("random", "random_available"):
             return kind
-        if kind == "preference":
-            raise NotImplementedError("the 'preference' policy is not implemented by the device planner")
+        if kind == "preference":                         # mcts.py:39-42: both keys are required there too
+            return ("preference", policy_config["action"], policy_config["ratio"])
         raise ValueError("Unknown policy type")

@@ -33,6 +33,8 @@ struct FiniteEnv {
     __device__ __forceinline__ void load_root(const MctsArgs& a, int tree, int li) { s = a.root_states[tree]; }
     __device__ __forceinline__ int avail(const MctsArgs& a, unsigned gmask) const { return (1 << a.cfg.n_actions) - 1; }
     __device__ __forceinline__ static int nth(int mask, int n) { return n; }
+    // position of `action` among the available actions in the env's order, or -1
+    __device__ __forceinline__ static int rank_of(int mask, int action) { return (action >= 0 && (mask >> action) & 1) ? action : -1; }
     __device__ __forceinline__ double step(const MctsArgs& a, int action, int li, unsigned gmask, float* gs, bool& term, bool& trunc) {
         const b2_finite_mdp& m = a.cfg.mdp;
         const double r = m.reward[(int64_t)s * m.n_actions + action];
@@ -55,6 +57,17 @@ struct HighwayEnv {
         return hw::avail_mask(ego_y, si);
     }
     __device__ __forceinline__ static int nth(int mask, int n) { return hw::nth_action(mask, n); }
+    __device__ __forceinline__ static int rank_of(int mask, int action) {
+        if (action < 0 || !((mask >> action) & 1)) return -1;
+        const int order[5] = {hw::A_IDLE, hw::A_LEFT, hw::A_RIGHT, hw::A_FASTER, hw::A_SLOWER};
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            if (order[i] == action) return k;
+            k += (mask >> order[i]) & 1;
+        }
+        return -1;
+    }
     __device__ __forceinline__ double step(const MctsArgs& a, int action, int li, unsigned gmask, float* gs, bool& term, bool& trunc) {
         return (double)hw::step(L, li, t, si, action, term, trunc, gmask, gs);
     }
@@ -103,15 +116,18 @@ __global__ void __launch_bounds__(128, B2_MCTS_MIN_BLOCKS) mcts_kernel(MctsArgs 
             const int amask = env.avail(a, gmask);
             if (active && in_sel && tr.first_child[nb + node] < 0) {
                 // expansion (mcts.py:151-154, :237-246): children for the policy's actions
-                const int pm = a.cfg.prior_policy == 0 ? amask : (1 << A) - 1;
+                const int pm = a.cfg.prior_policy != 1 ? amask : (1 << A) - 1;
                 const int n = __popc(pm);
                 if (writer) {
                     const double p = 1.0 / (double)n;
+                    const double* pt = nullptr;       // preference_policy (:76-97): host-made probabilities
+                    if (a.cfg.prior_policy == 2)
+                        pt = a.cfg.pref_prior + ((int64_t)n * (A + 1) + Env::rank_of(pm, a.cfg.prior_pref_action) + 1) * A;
                     for (int i = 0; i < n; ++i) {
                         const int c = n_nodes + i;
                         tr.parent[nb + c] = node; tr.first_child[nb + c] = -1; tr.count[nb + c] = 0;
-                        tr.meta[nb + c] = a.cfg.prior_policy == 0 ? Env::nth(pm, i) : i;
-                        tr.value[nb + c] = 0.0; tr.prior[nb + c] = p;
+                        tr.meta[nb + c] = a.cfg.prior_policy != 1 ? Env::nth(pm, i) : i;
+                        tr.value[nb + c] = 0.0; tr.prior[nb + c] = pt ? pt[i] : p;
                     }
                     tr.first_child[nb + node] = n_nodes;
                     tr.meta[nb + node] = (tr.meta[nb + node] & 0xff) | (n << 8);
@@ -152,14 +168,16 @@ __global__ void __launch_bounds__(128, B2_MCTS_MIN_BLOCKS) mcts_kernel(MctsArgs 
                     action = tr.meta[nb + child] & 0xff;
                 } else {
                     // rollout policy (mcts.py:171-172): choice(actions, 1, p)
-                    const int pm = a.cfg.rollout_policy == 0 ? amask : (1 << A) - 1;
+                    const int pm = a.cfg.rollout_policy != 1 ? amask : (1 << A) - 1;
                     const int n = __popc(pm);
                     const double u = rng.random();
-                    const double* cdf = a.cfg.uniform_cdf + (int64_t)n * A;
+                    const double* cdf = a.cfg.rollout_policy == 2
+                        ? a.cfg.pref_cdf + ((int64_t)n * (A + 1) + Env::rank_of(pm, a.cfg.rollout_pref_action) + 1) * A
+                        : a.cfg.uniform_cdf + (int64_t)n * A;
                     int idx = 0;
                     for (int i = 0; i < n; ++i) idx += cdf[i] <= u ? 1 : 0;   // searchsorted(side='right')
                     idx = min(idx, n - 1);
-                    action = a.cfg.rollout_policy == 0 ? Env::nth(pm, idx) : idx;
+                    action = a.cfg.rollout_policy != 1 ? Env::nth(pm, idx) : idx;
                 }
             }
             bool term, trunc;
@@ -226,8 +244,10 @@ extern "C" int b2_mcts_plan(const b2_mcts_config* cfg, const int32_t* root_state
     B2_REQUIRE(cfg->n_actions > 0 && cfg->n_actions <= MAX_BRANCH_MCTS, "n_actions must be in 1..8");
     B2_REQUIRE((int64_t)cfg->node_capacity >= 1 + (int64_t)cfg->episodes * cfg->n_actions, "node_capacity too small");
     B2_REQUIRE(cfg->gamma_pow && cfg->uniform_cdf, "gamma / cdf tables missing");
-    B2_REQUIRE(cfg->rollout_policy >= 0 && cfg->rollout_policy <= 1 && cfg->prior_policy >= 0 && cfg->prior_policy <= 1,
-               "policy must be 0 (random_available) or 1 (random)");
+    B2_REQUIRE(cfg->rollout_policy >= 0 && cfg->rollout_policy <= 2 && cfg->prior_policy >= 0 && cfg->prior_policy <= 2,
+               "policy must be 0 (random_available), 1 (random) or 2 (preference)");
+    B2_REQUIRE((cfg->prior_policy != 2 || cfg->pref_prior) && (cfg->rollout_policy != 2 || cfg->pref_cdf),
+               "preference policy tables missing");
     cudaStream_t stream = (cudaStream_t)stream_;
     MctsArgs a;
     a.cfg = *cfg; a.tree = *tree; a.root_states = root_states; a.rng = rng; a.plan = plan; a.result = result;

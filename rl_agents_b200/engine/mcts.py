@@ -2,9 +2,21 @@
 import numpy as np
 
 from rl_agents_b200 import _lib
-from rl_agents_b200.engine.tables import FiniteTables, gamma_tables, uniform_cdf_table
+from rl_agents_b200.engine.tables import FiniteTables, gamma_tables, preference_tables, uniform_cdf_table
 
-POLICIES = {"random_available": 0, "random": 1}
+POLICIES = {"random_available": 0, "random": 1, "preference": 2}
+
+
+def policy_spec(policy):
+    """"random" | "random_available" | ("preference", action, ratio) -> (kernel policy id, action, ratio)"""
+    if isinstance(policy, (tuple, list)):
+        kind, action, ratio = policy
+        if kind != "preference":
+            raise ValueError("Unknown policy type")
+        return POLICIES[kind], int(action), ratio
+    if policy not in ("random_available", "random"):
+        raise ValueError("Unknown policy type")
+    return POLICIES[policy], -1, 2
 
 
 def pcg64_words(gen):
@@ -68,9 +80,8 @@ class MCTSEngine(object):
         self.torch = torch
         self.lib = _lib.load()
         self.device = torch.device(device)
-        for pol in (rollout_policy, prior_policy):
-            if pol not in POLICIES:
-                raise ValueError("Unknown policy type")
+        rollout_id, rollout_action, rollout_ratio = policy_spec(rollout_policy)
+        prior_id, prior_action, prior_ratio = policy_spec(prior_policy)
         self.n_trees, self.n_actions = int(n_trees), int(n_actions)
         self.episodes, self.horizon = int(episodes), int(horizon)
         self.capacity = max(int(capacity or 0), 1 + self.episodes * self.n_actions)
@@ -86,10 +97,13 @@ class MCTSEngine(object):
         self.meta = torch.empty(shape, dtype=i32, device=self.device)
         self.value = torch.empty(shape, dtype=f64, device=self.device)
         self.prior = torch.empty(shape, dtype=f64, device=self.device)
+        self.pref_prior = torch.as_tensor(preference_tables(self.n_actions, prior_ratio)[0], device=self.device)
+        self.pref_cdf = torch.as_tensor(preference_tables(self.n_actions, rollout_ratio)[1], device=self.device)
         self.cfg = _lib.MCTSConfig(env_kind, self.n_trees, self.n_actions, self.episodes, self.horizon, self.capacity,
-                                   POLICIES[rollout_policy], POLICIES[prior_policy], float(temperature),
+                                   rollout_id, prior_id, float(temperature),
                                    self.gamma_pow.data_ptr(), self.cdf.data_ptr(),
-                                   self.tables.struct() if self.tables else _lib.FiniteMDP(), None)
+                                   self.tables.struct() if self.tables else _lib.FiniteMDP(),
+                                   prior_action, rollout_action, self.pref_prior.data_ptr(), self.pref_cdf.data_ptr(), None)
         self.resume = torch.zeros(self.n_trees, dtype=i32, device=self.device)
         self.tree = _lib.MCTSTree(*[t.data_ptr() for t in (self.parent, self.first_child, self.count, self.meta,
                                                            self.value, self.prior)])

@@ -31,6 +31,27 @@ def uniform_cdf_table(n_actions):
     return t
 
 
+def preference_tables(n_actions, ratio):
+    """MCTSAgent.preference_policy (mcts.py:76-97) for every (number of available actions n, position k-1 of
+    the preferred action among them; k = 0: not available -> uniform): the probabilities exactly as numpy
+    computes them there, and the cdf Generator.choice(actions, 1, p=p) searches.  Shape [(A+1), (A+1), A]."""
+    A = int(n_actions)
+    prior = np.ones((A + 1, A + 1, A), dtype=np.float64)
+    cdf = np.ones((A + 1, A + 1, A), dtype=np.float64)
+    for n in range(1, A + 1):
+        for k in range(0, n + 1):
+            if k == 0:
+                p = np.ones(n) / n
+            else:
+                p = np.ones(n) / (n - 1 + ratio)
+                p[k - 1] *= ratio
+            c = p.cumsum()
+            c /= c[-1]
+            prior[n, k, :n] = p
+            cdf[n, k, :n] = c
+    return prior, cdf
+
+
 class FiniteTables(object):
     """Device copy of a deterministic finite MDP (int32 transitions)."""
 

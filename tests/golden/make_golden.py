@@ -217,6 +217,28 @@ def main():
     mc["large1_terminal_b600_g0.9"] = run_mcts(finite(T, R, termx), {"budget": 600, "gamma": 0.9}, seed=1)
     out["mcts"] = mc
 
+    # ---------------- MCTS policies other than random_available (mcts.py:34-97) ----------------
+    pol = {}
+    pref_cfg = {"budget": 400, "gamma": 0.8,
+                "prior_policy": {"type": "preference", "action": 3, "ratio": 2},
+                "rollout_policy": {"type": "preference", "action": 1, "ratio": 3}}
+    pol["large1_preference_b400_g0.8"] = run_mcts(finite(), pref_cfg, seed=2)
+    rand_cfg = {"budget": 300, "gamma": 0.85, "prior_policy": {"type": "random"}, "rollout_policy": {"type": "random"}}
+    pol["large1_random_b300_g0.85"] = run_mcts(finite(), rand_cfg, seed=5)
+    out["mcts_policies"] = pol
+
+    # ---------------- closed-loop MCTS (mcts.py:125,147,267-273) on a deterministic env ----------------
+    agent = ref_mcts.MCTSAgent(finite(), {"budget": 400, "gamma": 0.8, "closed_loop": True})
+    agent.seed(3)
+    plan = agent.plan(0)
+    root = agent.planner.root
+    out["mcts_closed_loop"] = {
+        "config": {"budget": 400, "gamma": 0.8, "closed_loop": True}, "seed": 3,
+        "plan_actions": [int(a) for a in plan[0::2]],          # the reference interleaves observation keys
+        "plan_len": len(plan),
+        "root": [[int(a), int(c.count), float(c.value)] for a, c in root.children.items()],
+        "root_count": int(root.count), "root_value": float(root.value)}
+
     # ---------------- MCTS with step_strategy "subtree": two consecutive decisions ----------------
     def canonical(root):
         nodes, head = [root], 0

@@ -115,8 +115,8 @@ def test_agents_reject_unsupported_envs_and_options():
     stochastic = FiniteMDPEnv(np.full((3, 2, 3), 1 / 3), np.zeros((3, 2)), mode="stochastic")
     with pytest.raises(ValueError):
         DeterministicPlannerAgent(stochastic, {"budget": 10}).plan(None)
-    with pytest.raises(NotImplementedError):
-        MCTSAgent(finite_env(), {"closed_loop": True})
+    with pytest.raises(ValueError):
+        MCTSAgent(finite_env(), {"rollout_policy": {"type": "nope"}})
     with pytest.raises(KeyError):
         MCTSAgent(finite_env(), {"horizon": 5}).plan(None)        # mcts.py:116-118,180: episodes missing
 
@@ -199,3 +199,32 @@ def test_mcts_agent_subtree_strategy_matches_reference():
                                                                  d["prior"].tolist()])
         assert got == g["trees"][k], k
         env.step(plan[0])
+
+
+def test_mcts_agent_preference_and_random_policies_match_reference():
+    """prior / rollout policies other than random_available (mcts.py:34-97): goldens from the reference."""
+    from rl_agents_b200.agents.tree_search.mcts import MCTSAgent
+    for key, g in G["mcts_policies"].items():
+        agent = MCTSAgent(finite_env(), dict(g["config"]))
+        agent.seed(g["seed"])
+        assert agent.plan(None) == g["plan"], key
+        d = agent.planner.last_tree.tree_dict(0)
+        full = "n_nodes" not in g["tree"]
+        k = len(g["tree"]["parent"]) if full else 64
+        assert d["parent"][:k].tolist() == g["tree"]["parent"][:k] and d["count"][:k].tolist() == g["tree"]["count"][:k]
+        assert np.array_equal(d["value"][:k], np.array(g["tree"]["value"][:k]))
+        assert np.array_equal(d["prior"][:k], np.array(g["tree"]["prior"][:k]))
+
+
+def test_mcts_agent_closed_loop_on_a_deterministic_env_matches_reference():
+    """closed_loop=True in the reference adds one observation-keyed node per action node on a deterministic
+    env; statistics and the recommended actions are those of the open-loop search."""
+    from rl_agents_b200.agents.tree_search.mcts import MCTSAgent
+    g = G["mcts_closed_loop"]
+    agent = MCTSAgent(finite_env(), dict(g["config"]))
+    agent.seed(g["seed"])
+    assert agent.plan(0) == g["plan_actions"]
+    d = agent.planner.last_tree.tree_dict(0)
+    fc, n = int(d["first_child"][0]), int(d["n_children"][0])
+    assert [[int(d["action"][c]), int(d["count"][c]), float(d["value"][c])] for c in range(fc, fc + n)] == g["root"]
+    assert int(d["count"][0]) == g["root_count"] and float(d["value"][0]) == g["root_value"]

@@ -264,3 +264,32 @@ def test_vi_and_opd_agree_on_terminal_semantics():
             i = tree.parent[i]
         return g
     assert abs(max(path_return(i) for i in done_nodes if tree.depth[i] == 3) - best) < 1e-12
+
+
+def test_mcts_policies_and_closed_loop_goldens():
+    """The oracle's policies (mcts.py:34-97) against the reference, and: on a deterministic env the
+    reference's closed_loop search has the statistics of the open-loop one."""
+    for key, g in G["mcts_policies"].items():
+        plan, t = planners.mcts_plan(finite(), g["episodes"], g["horizon"], g["config"]["gamma"], g["temperature"],
+                                     np_random(g["seed"]), prior_policy=g["config"]["prior_policy"],
+                                     rollout_policy=g["config"]["rollout_policy"])
+        assert plan == g["plan"], key
+        assert_tree_matches(tree_dict(t, ["value", "prior"]), g["tree"], ["value", "prior"])
+    g = G["mcts_closed_loop"]
+    episodes, horizon = planners.olop_allocation(g["config"]["budget"], g["config"]["gamma"])
+    plan, t = planners.mcts_plan(finite(), episodes, horizon, g["config"]["gamma"], 10.0, np_random(g["seed"]))
+    assert plan == g["plan_actions"] and g["plan_len"] == 2 * len(plan) - 1
+    assert [[t.action[c], t.count[c], t.value[c]] for c in t.children(0)] == g["root"]
+    assert t.count[0] == g["root_count"] and t.value[0] == g["root_value"]
+
+
+def test_preference_tables_follow_numpy():
+    from rl_agents_b200.engine.tables import preference_tables
+    prior, cdf = preference_tables(5, 3)
+    p = np.ones(4) / (4 - 1 + 3)
+    p[2] *= 3
+    assert np.array_equal(prior[4, 3, :4], p)
+    c = p.cumsum()
+    c /= c[-1]
+    assert np.array_equal(cdf[4, 3, :4], c)
+    assert np.array_equal(prior[3, 0, :3], np.ones(3) / 3)
