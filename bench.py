@@ -713,6 +713,28 @@ def other_paths(a, dev, world, rank):
         torch.cuda.empty_cache()
     except Exception as ex:
         out["mcts_c3_root_parallel"] = {"error": repr(ex)[:300]}
+    # ---- C3 as ONE decision searched by the whole GPU (rank 0's GPU; no collective): wavefront MCTS ----
+    try:
+        from rl_agents_b200.engine.mcts import MCTSWaveEngine
+        rows = []
+        scene = torch.tensor(make_scene(0), dtype=torch.int32, device=dev)
+        for width in (256, 512, 1024):
+            eng = MCTSWaveEngine(_lib.ENV_HIGHWAY, N_ACTIONS, 4096, 20, 0.8, 10.0, width, device=dev)
+            ms = timed_ms(lambda: eng.plan(scene, 0), reps=5)
+            eng.plan(scene, 0)
+            plan, res = eng.finish()
+            rows.append({"width": width, "ms_per_decision": ms, "episodes_per_s": 4096 / (ms * 1e-3),
+                         "env_steps": int(res[2]), "env_steps_per_s": int(res[2]) / (ms * 1e-3), "waves": int(res[3]),
+                         "recommended_action": plan[0] if plan else None})
+            del eng
+        out["mcts_c3_wavefront"] = {
+            "workload": "C3: MCTS on HighwayLite, 4096 episodes x horizon 20, ONE tree, waves of `width` episodes "
+                        "(b2_mcts_plan_wave; specification oracle/planners.py::mcts_plan_wavefront, bit-exact)",
+            "strict_reference_order_ms": "2340 (one sequential chain of 81 920 env steps; profiles/r01_misc_measurements.json)",
+            "rows": rows}
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["mcts_c3_wavefront"] = {"error": repr(ex)[:300]}
     # ---- C5-sized: ONE OPD decision, budget 1e6, sub-tree sharded (ShardedOPD, one all_reduce(MAX)) ----
     try:
         sh = D.ShardedOPD(1000000, 0.8, device=dev)
@@ -789,17 +811,19 @@ def single_decision_latency(a, dev, reps=5):
                      "root_value_lower_gap_vs_strict_max": float(max(gaps)),
                      "root_value_lower_strict_mean": float(np.mean([l for _, l in strict]))})
         del eng
-    big = {}
-    try:
-        eng = OPDWaveEngine(_lib.ENV_HIGHWAY, N_ACTIONS, 1000000, a.gamma, 1024, device=dev)
-        ms = med_ms(lambda: eng.plan(scenes[0]))
-        eng.plan(scenes[0])
-        _, res = eng.finish([np.random.default_rng(0)])
-        big = {"budget": 1000000, "expansions": 200000, "width": 1024, "ms": float(ms), "waves": int(res[0, 7]),
-               "expansions_per_s": 200000 / (ms * 1e-3), "max_depth": int(res[0, 2])}
-        del eng
-    except Exception as e:
-        big = {"error": str(e)[:200]}
+    big = []
+    for width in (1024, 4096):
+        try:
+            eng = OPDWaveEngine(_lib.ENV_HIGHWAY, N_ACTIONS, 1000000, a.gamma, width, device=dev)
+            ms = med_ms(lambda: eng.plan(scenes[0]))
+            eng.plan(scenes[0])
+            _, res = eng.finish([np.random.default_rng(0)])
+            big.append({"budget": 1000000, "expansions": 200000, "width": width, "ms": float(ms), "waves": int(res[0, 7]),
+                        "expansions_per_s": 200000 / (ms * 1e-3), "max_depth": int(res[0, 2]),
+                        "root_value_lower": float(eng.lower[0, 0].item())})
+            del eng
+        except Exception as e:
+            big.append({"width": width, "error": str(e)[:200]})
     return {"workload": "ONE C2 decision: OPD on HighwayLite, budget %d, gamma %g" % (a.budget, a.gamma),
             "specification": "oracle/planners.py::opd_plan_wavefront (bit-exact, tests/test_gpu_wave.py); width 1 = reference",
             "rows": rows, "budget_1e6_decision": big}

@@ -161,7 +161,7 @@ int mcts_highway_plan_wave(const int32_t* root_words, int episodes, int horizon,
                 for (int i = 0; i < k; ++i) {
                     const int c = fc + i;
                     const double v = count[c] > 0 ? ((double)vsum[c] / FIX) / (double)count[c] : 0.0;
-                    sc[i] = v + temperature * (double)k * prior / (double)(count[c] + virt[c] + 1);
+                    sc[i] = v + temperature * (double)k * prior * (1.0 / (double)(count[c] + virt[c] + 1));
                     if (sc[i] > best) { best = sc[i]; ties = 1; } else if (sc[i] == best) ++ties;
                 }
                 int pick = wave_random(seed, e, depth, 0, ties), sel = 0;

@@ -390,7 +390,9 @@ def mcts_plan_wavefront(env, episodes, horizon, gamma, temperature, width, seed)
                 kids = list(t.children(node))
                 n = len(kids)
                 prior = 1.0 / n
-                x = [value(c) + temperature * n * prior / (t.count[c] + virtual.get(c, 0) + 1) for c in kids]
+                # the reference's score (mcts.py:275-286) with the division by (count + 1) written as a
+                # multiplication by the reciprocal 1.0 / (count + virtual + 1)
+                x = [value(c) + temperature * n * prior * (1.0 / (t.count[c] + virtual.get(c, 0) + 1)) for c in kids]
                 best = max(x)
                 ties = [i for i in range(n) if x[i] == best]
                 child = kids[ties[wave_random(seed, e, depth, 0, len(ties))]]

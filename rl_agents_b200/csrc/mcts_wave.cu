@@ -42,6 +42,7 @@ struct Args {
     int32_t* paths;          // [width, horizon] node reached at depth h+1
     int32_t* plen;           // [width] selection depth
     int32_t* expands;        // [width] 1: this episode creates the children of its leaf
+    double* recip;           // [episodes + width + 2] 1.0 / k (filled at kernel start)
     int8_t* plan;
     int32_t* result;
 };
@@ -56,7 +57,7 @@ __device__ __forceinline__ int wave_random(unsigned long long seed, int episode,
     const unsigned long long key = seed + (unsigned long long)episode * 0x9E3779B97F4A7C15ull +
                                    (unsigned long long)(step + 1) * 0xD1B54A32D192ED03ull +
                                    (unsigned long long)stream * 0x8CB92BA72F3D8DD7ull;
-    return (int)((splitmix64(key) >> 33) % (unsigned long long)n);
+    return (int)((unsigned)(splitmix64(key) >> 33) % (unsigned)n);    // 31-bit value: a 32-bit modulo gives the same result
 }
 
 __device__ __forceinline__ void grid_barrier(Control* ctl, unsigned n_ctas) {
@@ -77,16 +78,92 @@ __device__ __forceinline__ void grid_barrier(Control* ctl, unsigned n_ctas) {
     __syncthreads();
 }
 
+// order-preserving image of a finite double as a signed 64-bit integer (+0 and -0 coincide)
+__device__ __forceinline__ long long score_key(double x) {
+    const long long b = __double_as_longlong(x + 0.0);
+    return b >= 0 ? b : (long long)(0x8000000000000000ull - (unsigned long long)b);
+}
+
+constexpr int BIG_MIN = 16;                 // arrivals from which a segment gets a precomputed score table
+constexpr int MAX_BIG = MAX_WIDTH / BIG_MIN;
+constexpr int TABLE_KEYS = 6144;            // 48 KB of dynamic shared memory
+
 struct SelShared {
     unsigned short order[2][MAX_WIDTH];
     unsigned char pick[MAX_WIDTH];
     int seg_node[2][MAX_WIDTH];
     unsigned short seg_start[2][MAX_WIDTH], seg_len[2][MAX_WIDTH];
     int nseg[2];
+    int n_big, tab_used;
+    int big_seg[MAX_BIG], big_off[MAX_BIG], big_fc[MAX_BIG];
+    unsigned char big_n[MAX_BIG];
+    double big_val[MAX_BIG][MAX_A];
+    int big_cnt[MAX_BIG][MAX_A];
 };
 
+// One segment's arrivals, in episode order: pick the best child by (score, counter-based tie-break), bump its
+// virtual count, record the path; then split the segment into the children's segments (stable partition).
+// `key_of(c, k)` is the order-preserving image of child c's score after k virtual visits.
+template <typename KeyOf>
+__device__ __forceinline__ void route_segment(const Args& a, SelShared& sh, int cur, int nxt, int w0, int d, int start,
+                                              int m, int fc, int n, KeyOf key_of) {
+    const int H = a.cfg.horizon;
+    long long key[MAX_A];
+    int vc[MAX_A];
+#pragma unroll
+    for (int c = 0; c < MAX_A; ++c) {
+        vc[c] = 0;
+        key[c] = c < n ? key_of(c, 0) : (long long)0x8000000000000000ull;      // below every real score
+    }
+    for (int i = 0; i < m; ++i) {
+        const int j = sh.order[cur][start + i];
+        long long best = key[0];
+#pragma unroll
+        for (int c = 1; c < MAX_A; ++c) best = key[c] > best ? key[c] : best;
+        int ties = 0;
+#pragma unroll
+        for (int c = 0; c < MAX_A; ++c) ties += key[c] == best ? 1 : 0;
+        int pick = ties > 1 ? wave_random(a.cfg.seed, w0 + j, d, 0, ties) : 0, sel = 0;
+#pragma unroll
+        for (int c = 0; c < MAX_A; ++c) {
+            if (key[c] == best) {
+                if (pick == 0) sel = c;
+                --pick;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < MAX_A; ++c) {
+            if (c == sel) {
+                vc[c] += 1;
+                key[c] = key_of(c, vc[c]);
+            }
+        }
+        sh.pick[start + i] = (unsigned char)sel;
+        a.paths[(int64_t)j * H + d] = fc + sel;
+    }
+    int cstart[MAX_A];
+    int run = start;
+#pragma unroll
+    for (int c = 0; c < MAX_A; ++c) {
+        cstart[c] = run;
+        if (c < n && vc[c] > 0) {
+            const int q = atomicAdd(&sh.nseg[nxt], 1);
+            sh.seg_node[nxt][q] = fc + c;
+            sh.seg_start[nxt][q] = (unsigned short)run;
+            sh.seg_len[nxt][q] = (unsigned short)vc[c];
+        }
+        run += c < n ? vc[c] : 0;
+    }
+    for (int i = 0; i < m; ++i) {
+        const int sel = sh.pick[start + i];
+#pragma unroll
+        for (int c = 0; c < MAX_A; ++c)
+            if (c == sel) sh.order[nxt][cstart[c]++] = sh.order[cur][start + i];
+    }
+}
+
 // CTA 0: the selections of the episodes [w0, w0 + nw) -> paths / plen / expands
-__device__ void select_wave(const Args& a, SelShared& sh, int w0, int nw) {
+__device__ void select_wave(const Args& a, SelShared& sh, long long* table, int w0, int nw) {
     const int tid = threadIdx.x;
     const b2_mcts_wave_tree& tr = a.tree;
     const int H = a.cfg.horizon;
@@ -95,6 +172,7 @@ __device__ void select_wave(const Args& a, SelShared& sh, int w0, int nw) {
     if (tid == 0) {
         sh.seg_node[0][0] = 0; sh.seg_start[0][0] = 0; sh.seg_len[0][0] = (unsigned short)nw;
         sh.nseg[0] = 1; sh.nseg[1] = 0;
+        sh.n_big = 0; sh.tab_used = 0;
     }
     __syncthreads();
     int cur = 0;
@@ -102,6 +180,11 @@ __device__ void select_wave(const Args& a, SelShared& sh, int w0, int nw) {
         const int nseg = sh.nseg[cur];
         if (nseg == 0) break;
         const int nxt = cur ^ 1;
+#ifdef B2_MWAVE_DEBUG
+        const long long dbg_t0 = clock64();
+#endif
+        // ---- A: one thread per segment.  Small segments are routed right here (scores computed on the fly);
+        //         segments with many arrivals register for a precomputed score table ----
         for (int s = tid; s < nseg; s += THREADS) {
             const int node = sh.seg_node[cur][s], start = sh.seg_start[cur][s], m = sh.seg_len[cur][s];
             const int fc = d < H ? __ldcg(tr.first_child + node) : -1;
@@ -115,74 +198,62 @@ __device__ void select_wave(const Args& a, SelShared& sh, int w0, int nw) {
                 continue;
             }
             const int n = (__ldcg(tr.meta + node) >> 8) & 0xff;
-            const double prior = 1.0 / (double)n;
-            const double tn = T * (double)n;
-            double val[MAX_A], sc[MAX_A];
-            int cnt[MAX_A], vc[MAX_A];
+            double val[MAX_A];
+            int cnt[MAX_A];
 #pragma unroll
             for (int c = 0; c < MAX_A; ++c) {
+                val[c] = 0.0; cnt[c] = 0;
                 if (c < n) {
                     cnt[c] = __ldcg(tr.count + fc + c);
                     const long long vs = __ldcg(tr.vsum + fc + c);
                     val[c] = cnt[c] > 0 ? ((double)vs / FIX_SCALE) / (double)cnt[c] : 0.0;
-                    vc[c] = 0;
-                    sc[c] = val[c] + tn * prior / (double)(cnt[c] + 1);
                 }
             }
-            for (int i = 0; i < m; ++i) {
-                const int j = sh.order[cur][start + i];
-                double best = -INFINITY;
-                int ties = 0;
-#pragma unroll
-                for (int c = 0; c < MAX_A; ++c) {
-                    if (c < n) {
-                        if (sc[c] > best) { best = sc[c]; ties = 1; }
-                        else if (sc[c] == best) ++ties;
-                    }
-                }
-                int pick = ties > 1 ? wave_random(a.cfg.seed, w0 + j, d, 0, ties) : 0, sel = 0;
-#pragma unroll
-                for (int c = 0; c < MAX_A; ++c) {
-                    if (c < n && sc[c] == best) {
-                        if (pick == 0) sel = c;
-                        --pick;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < MAX_A; ++c) {
-                    if (c == sel) {
-                        vc[c] += 1;
-                        sc[c] = val[c] + tn * prior / (double)(cnt[c] + vc[c] + 1);
-                    }
-                }
-                sh.pick[start + i] = (unsigned char)sel;
-                a.paths[(int64_t)j * H + d] = fc + sel;
+            int b = -1, off = 0;
+            if (m >= BIG_MIN) {
+                off = atomicAdd(&sh.tab_used, n * (m + 1));
+                if (off + n * (m + 1) <= TABLE_KEYS) b = atomicAdd(&sh.n_big, 1);
             }
-            // the children's segments: the stable partition of [start, start + m)
-            int cstart[MAX_A];
-            int run = start;
+            if (b >= 0) {
+                sh.big_seg[b] = s; sh.big_off[b] = off; sh.big_fc[b] = fc; sh.big_n[b] = (unsigned char)n;
 #pragma unroll
-            for (int c = 0; c < MAX_A; ++c) {
-                if (c < n) {
-                    cstart[c] = run;
-                    if (vc[c] > 0) {
-                        const int q = atomicAdd(&sh.nseg[nxt], 1);
-                        sh.seg_node[nxt][q] = fc + c;
-                        sh.seg_start[nxt][q] = (unsigned short)run;
-                        sh.seg_len[nxt][q] = (unsigned short)vc[c];
-                    }
-                    run += vc[c];
-                }
+                for (int c = 0; c < MAX_A; ++c) { sh.big_val[b][c] = val[c]; sh.big_cnt[b][c] = cnt[c]; }
+                continue;
             }
-            for (int i = 0; i < m; ++i) {
-                const int sel = sh.pick[start + i];
+            const double tnp = T * (double)n * (1.0 / (double)n);
+            route_segment(a, sh, cur, nxt, w0, d, start, m, fc, n, [&](int c, int k) {
+                double v = 0.0;
+                int base = 0;
 #pragma unroll
-                for (int c = 0; c < MAX_A; ++c)
-                    if (c == sel) sh.order[nxt][cstart[c]++] = sh.order[cur][start + i];
+                for (int q = 0; q < MAX_A; ++q)
+                    if (q == c) { v = val[q]; base = cnt[q]; }
+                return score_key(v + tnp * a.recip[base + k + 1]);
+            });
+        }
+        __syncthreads();
+        // ---- B: the score tables of the big segments, filled by the whole CTA: child c after k virtual visits ----
+        const int n_big = sh.n_big;
+        for (int b = 0; b < n_big; ++b) {
+            const int s = sh.big_seg[b], m = sh.seg_len[cur][s], n = sh.big_n[b], off = sh.big_off[b];
+            const double tnp = T * (double)n * (1.0 / (double)n);
+            for (int idx = tid; idx < n * (m + 1); idx += THREADS) {
+                const int c = idx / (m + 1), k = idx - c * (m + 1);
+                table[off + idx] = score_key(sh.big_val[b][c] + tnp * a.recip[sh.big_cnt[b][c] + k + 1]);
             }
         }
         __syncthreads();
-        if (tid == 0) sh.nseg[cur] = 0;
+        // ---- C: one thread per big segment walks its arrivals with table look-ups only ----
+        if (tid < n_big) {
+            const int s = sh.big_seg[tid], start = sh.seg_start[cur][s], m = sh.seg_len[cur][s];
+            const long long* tab = table + sh.big_off[tid];
+            route_segment(a, sh, cur, nxt, w0, d, start, m, sh.big_fc[tid], sh.big_n[tid],
+                          [&](int c, int k) { return tab[c * (m + 1) + k]; });
+        }
+        __syncthreads();
+#ifdef B2_MWAVE_DEBUG
+        if (tid == 0 && w0 == 8 * a.cfg.width) printf("level %d nseg %d big %d cycles %lld\n", d, nseg, n_big, clock64() - dbg_t0);
+#endif
+        if (tid == 0) { sh.nseg[cur] = 0; sh.n_big = 0; sh.tab_used = 0; }
         cur = nxt;
         __syncthreads();
     }
@@ -199,6 +270,7 @@ __device__ __forceinline__ void backup(const Args& a, int j, int reached, double
 }
 
 __global__ void __launch_bounds__(THREADS, 1) mcts_wave_kernel(Args a) {
+    extern __shared__ long long score_table[];
     __shared__ SelShared sh;
     __shared__ float hw_scratch[GROUPS][hw::SCRATCH_FLOATS];
     const int tid = threadIdx.x, lane = tid & 31, li = tid & 15;
@@ -215,6 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) mcts_wave_kernel(Args a) {
         tr.meta[i] = 0xff;
         tr.vsum[i] = 0;
     }
+    for (int i = blockIdx.x * THREADS + tid; i < E + W + 2; i += THREADS * (int)n_ctas) a.recip[i] = 1.0 / (double)i;
     grid_barrier(ctl, n_ctas);
     long long tp = clock64();
     auto lap = [&](int slot) {
@@ -223,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1) mcts_wave_kernel(Args a) {
     int env_steps = 0;
     for (int w0 = 0; w0 < E; w0 += W) {
         const int nw = min(W, E - w0);
-        if (blockIdx.x == 0) select_wave(a, sh, w0, nw);
+        if (blockIdx.x == 0) select_wave(a, sh, score_table, w0, nw);
         lap(0);
         grid_barrier(ctl, n_ctas);
         lap(1);
@@ -372,14 +445,15 @@ __global__ void __launch_bounds__(THREADS, 1) mcts_wave_kernel(Args a) {
 }
 
 static int64_t align_up(int64_t x) { return (x + 255) & ~(int64_t)255; }
-struct Layout { int64_t ctl, paths, plen, expands, total; };
+struct Layout { int64_t ctl, paths, plen, expands, recip, total; };
 static Layout make_layout(const b2_mcts_wave_config* c) {
     Layout l;
     l.ctl = 0;
     l.paths = align_up(sizeof(Control));
     l.plen = l.paths + align_up((int64_t)c->width * (c->horizon > 0 ? c->horizon : 1) * 4);
     l.expands = l.plen + align_up((int64_t)c->width * 4);
-    l.total = l.expands + align_up((int64_t)c->width * 4);
+    l.recip = l.expands + align_up((int64_t)c->width * 4);
+    l.total = l.recip + align_up(((int64_t)c->episodes + c->width + 2) * 8);
     return l;
 }
 
@@ -420,15 +494,18 @@ extern "C" int b2_mcts_plan_wave(const b2_mcts_wave_config* cfg, const int32_t* 
     a.paths = (int32_t*)(ws + l.paths);
     a.plen = (int32_t*)(ws + l.plen);
     a.expands = (int32_t*)(ws + l.expands);
+    a.recip = (double*)(ws + l.recip);
     a.plan = plan; a.result = result;
     B2_CUDA_CHECK(cudaMemsetAsync(a.ctl, 0, sizeof(mwave::Control), stream));
+    const size_t smem = (size_t)mwave::TABLE_KEYS * 8;
+    B2_CUDA_CHECK(cudaFuncSetAttribute(mwave::mcts_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    B2_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mwave::mcts_wave_kernel, mwave::THREADS, 0));
+    B2_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mwave::mcts_wave_kernel, mwave::THREADS, smem));
     B2_REQUIRE(per_sm >= 1, "wave kernel does not fit on an SM");
     int grid = sm_count();
     if (cfg->max_ctas > 0 && cfg->max_ctas < grid) grid = cfg->max_ctas;
     void* params[] = {&a};
     B2_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)mwave::mcts_wave_kernel, dim3(grid), dim3(mwave::THREADS), params,
-                                              0, stream));
+                                              smem, stream));
     return B2_OK;
 }

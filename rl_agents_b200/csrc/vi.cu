@@ -371,6 +371,55 @@ __global__ void __launch_bounds__(128) vi_sweep_dense_kernel(SweepArgs g) {
     if ((tid & 31) == 0 && bad) atomicAdd(g.viol + g.sweep, bad);
 }
 
+// Dense stochastic mode, cooperative: an 8-lane group per (s,a) row.  numpy's pairwise sum keeps eight strided
+// accumulators r[j] += a[i + j] over a block of <= 128 elements and combines them as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)): lane j of the group IS accumulator j, so the row of P is read in
+// coalesced 64-byte pieces (the one-thread-per-row kernel reads with a stride of S doubles), and the fixed
+// combination tree is an xor-butterfly (fp addition commutes, so every lane ends with the same bits).
+// Blocks longer than 128 split in halves exactly as numpy does (n2 = n/2 rounded down to a multiple of 8).
+template <typename Load>
+__device__ __noinline__ double np_pairwise_sum_group(Load a, int lo, int n, int lane8, unsigned gmask) {
+    if (n < 8) {
+        double res = 0.;
+        for (int i = 0; i < n; ++i) res += a(lo + i);
+        return res;
+    }
+    if (n <= 128) {
+        double r = a(lo + lane8);
+        const int body = n - (n % 8);
+        for (int i = 8; i < body; i += 8) r += a(lo + i + lane8);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) r = r + __shfl_xor_sync(gmask, r, o);
+        for (int i = body; i < n; ++i) r += a(lo + i);
+        return r;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const double left = np_pairwise_sum_group(a, lo, n2, lane8, gmask);
+    return left + np_pairwise_sum_group(a, lo + n2, n - n2, lane8, gmask);
+}
+
+__global__ void __launch_bounds__(256) vi_sweep_dense_group_kernel(SweepArgs g) {
+    if (g.sweep > 0 && g.viol[g.sweep - 1] == 0) return;
+    const int tid = threadIdx.x, lane8 = tid & 7;
+    const unsigned gmask = 0xffu << (tid & 24);
+    const int64_t n_rows = g.rows * g.A;
+    const int64_t row_raw = (int64_t)blockIdx.x * 32 + (tid >> 3);
+    const bool live = row_raw < n_rows;
+    const int64_t row = live ? row_raw : n_rows - 1;       // idle groups shadow the last row, never store
+    const double* p = g.P + row * (int64_t)g.B;
+    double nv = np_pairwise_sum_group([&](int i) { return p[i] * g.v_in[i]; }, 0, g.B, lane8, gmask);
+    int bad = 0;
+    if (live && lane8 == 0) {
+        if (g.term[row / g.A]) nv = 0.0;
+        const double q = g.R[row] + g.gamma * nv;
+        if (!np_isclose(g.q_old[row], q, g.rtol, g.atol)) bad = 1;
+        g.q_new[row] = q;
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((tid & 31) == 0 && bad) atomicAdd(g.viol + g.sweep, bad);
+}
+
 // V' = max_a Q' for the dense mode (rows may straddle CTAs there)
 __global__ void vi_rowmax_kernel(SweepArgs g) {
     if (g.sweep > 0 && g.viol[g.sweep - 1] == 0) return;
@@ -438,7 +487,10 @@ extern "C" int b2_vi_sweep(const b2_vi_problem* p, const double* v_in, const dou
         B2_REQUIRE(p->n_next == p->n_states, "stochastic mode: n_next must equal n_states");
         g.P = (const double*)p->transition; g.N = nullptr; g.B = (int)p->n_states; g.tile_states = 0;
         const int64_t n_rows = g.rows * g.A;
-        vi_sweep_dense_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, stream>>>(g);
+        if (p->reserved == 1)     // one thread per row (kept selectable; the group kernel is the default)
+            vi_sweep_dense_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, stream>>>(g);
+        else
+            vi_sweep_dense_group_kernel<<<(unsigned)((n_rows + 31) / 32), 256, 0, stream>>>(g);
         vi_rowmax_kernel<<<(unsigned)((g.rows + 255) / 256), 256, 0, stream>>>(g);
         B2_CUDA_CHECK(cudaGetLastError());
         return B2_OK;

@@ -209,6 +209,25 @@ def test_vi_kernel_variants_vs_oracle(mode, S, A, B, seed, kernel):
     assert np.array_equal(q.cpu().numpy(), q_ref)
 
 
+@pytest.mark.parametrize("S,A,seed", [(100, 4, 0), (5, 2, 1), (129, 3, 2), (300, 2, 3), (1000, 4, 4), (2051, 1, 5)])
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_vi_dense_kernels_follow_numpy_pairwise_order(S, A, seed, kernel):
+    """Dense (stochastic) mode: the 8-lanes-per-row kernel (default) and the thread-per-row kernel both
+    reproduce numpy's pairwise summation bit for bit -- < 8, <= 128 and recursive-halving row lengths."""
+    from rl_agents_b200.engine.vi import VIEngine
+    rng = np.random.default_rng(seed)
+    P = rng.uniform(size=(S, A, S))
+    P /= P.sum(axis=-1, keepdims=True)
+    R = rng.uniform(size=(S, A))
+    term = rng.uniform(size=S) < 0.05
+    q_ref, sweeps_ref = planners.value_iteration("stochastic", P, R, term, 0.9, 12)
+    eng = VIEngine("stochastic", P, R, term, gamma=0.9)
+    eng.problem.reserved = kernel
+    q, sweeps = eng.solve(12)
+    assert sweeps == sweeps_ref
+    assert np.array_equal(q.cpu().numpy(), q_ref)
+
+
 def test_vi_early_exit_returns_previous_iterate():
     from rl_agents_b200.engine.vi import VIEngine
     T, R = oenvs.garnet(400, 4, 1, seed=9, deterministic=True)
