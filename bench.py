@@ -737,7 +737,7 @@ def other_paths(a, dev, world, rank):
         out["mcts_c3_wavefront"] = {"error": repr(ex)[:300]}
     # ---- C5-sized: ONE OPD decision, budget 1e6, sub-tree sharded (ShardedOPD, one all_reduce(MAX)) ----
     try:
-        sh = D.ShardedOPD(1000000, 0.8, device=dev)
+        sh = D.ShardedOPD(1000000, 0.8, device=dev, wave_width=1024)
         scene_np = make_scene(0)
         sync()
         t0 = time.perf_counter()
@@ -751,7 +751,7 @@ def other_paths(a, dev, world, rank):
         dt = min(dt, max_over_ranks(time.perf_counter() - t0))
         out["opd_1e6_subtree_sharded"] = {
             "workload": "ONE OPD decision on HighwayLite (C5's env intersection-v0 is not modelled), budget 1e6, gamma 0.8, "
-                        "%d sub-trees dealt over %d GPU(s), strict best-first inside each" % (r["n_subtrees"], world),
+                        "%d sub-trees dealt over %d GPU(s), each searched by its rank's whole GPU in waves of 1024 leaves" % (r["n_subtrees"], world),
             "s_per_decision": dt, "expansions_per_s": 200000 / dt, "action": int(r["action"]),
             "root_lower": float(r["root_lower"]),
             "collective": None if world == 1 else "one all_reduce(MAX) of the [n_subtrees, 2] bounds"}

@@ -14,25 +14,47 @@
 namespace b2 {
 
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src):
-// < 8 sequential; <= 128 eight strided accumulators; else split in halves.
+// < 8 sequential; <= 128 eight strided accumulators; else split in halves (n2 = n/2 rounded down to a multiple
+// of 8) and add the two halves' sums.  The recursion is unrolled on an explicit stack (device recursion would
+// need a per-thread stack the compiler cannot bound): leaf(lo, n) sums one block of n <= 128 elements.
+template <typename Leaf>
+__device__ __forceinline__ double np_pairwise_tree(Leaf leaf, int lo0, int n0) {
+    int lo_s[26], n_s[26];
+    double left_s[26];
+    unsigned char st_s[26];
+    int sp = 0;
+    lo_s[0] = lo0; n_s[0] = n0; st_s[0] = 0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int lo = lo_s[sp], n = n_s[sp];
+        if (n <= 128) { ret = leaf(lo, n); --sp; continue; }
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        if (st_s[sp] == 0) { st_s[sp] = 1; ++sp; lo_s[sp] = lo; n_s[sp] = n2; st_s[sp] = 0; }
+        else if (st_s[sp] == 1) { left_s[sp] = ret; st_s[sp] = 2; ++sp; lo_s[sp] = lo + n2; n_s[sp] = n - n2; st_s[sp] = 0; }
+        else { ret = left_s[sp] + ret; --sp; }
+    }
+    return ret;
+}
+
+template <typename Load>
+__device__ __forceinline__ double np_pairwise_leaf(Load a, int lo, int n) {   // 8 <= n <= 128
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a(lo + j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += a(lo + i + j);
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a(lo + i);
+    return res;
+}
+
 template <typename Load>
 __device__ __noinline__ double np_pairwise_sum_big(Load a, int lo, int n) {
-    if (n <= 128) {
-        double r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = a(lo + j);
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] += a(lo + i + j);
-        }
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += a(lo + i);
-        return res;
-    }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return np_pairwise_sum_big(a, lo, n2) + np_pairwise_sum_big(a, lo + n2, n - n2);
+    return np_pairwise_tree([&](int l, int m) { return np_pairwise_leaf(a, l, m); }, lo, n);
 }
 
 template <typename Load>
@@ -384,19 +406,15 @@ __device__ __noinline__ double np_pairwise_sum_group(Load a, int lo, int n, int 
         for (int i = 0; i < n; ++i) res += a(lo + i);
         return res;
     }
-    if (n <= 128) {
-        double r = a(lo + lane8);
-        const int body = n - (n % 8);
-        for (int i = 8; i < body; i += 8) r += a(lo + i + lane8);
+    return np_pairwise_tree([&](int l, int m) {
+        double r = a(l + lane8);
+        const int body = m - (m % 8);
+        for (int i = 8; i < body; i += 8) r += a(l + i + lane8);
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) r = r + __shfl_xor_sync(gmask, r, o);
-        for (int i = body; i < n; ++i) r += a(lo + i);
+        for (int i = body; i < m; ++i) r += a(l + i);
         return r;
-    }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    const double left = np_pairwise_sum_group(a, lo, n2, lane8, gmask);
-    return left + np_pairwise_sum_group(a, lo + n2, n - n2, lane8, gmask);
+    }, lo, n);
 }
 
 __global__ void __launch_bounds__(256) vi_sweep_dense_group_kernel(SweepArgs g) {

@@ -316,9 +316,13 @@ class ShardedOPD(object):
     evenly instead of greedily); with world == 1 the same decomposition runs on one GPU, which is
     what the parity test compares against."""
 
-    def __init__(self, budget, gamma, terminal_reward=0.0, group=None, device="cuda", max_depth=3):
+    def __init__(self, budget, gamma, terminal_reward=0.0, group=None, device="cuda", max_depth=3, wave_width=0):
+        """wave_width = 0: every sub-tree is searched in the reference's strict best-first order (one CTA per
+        sub-tree, all of a rank's sub-trees in one launch).  wave_width = K > 0: every sub-tree is searched by
+        the rank's whole GPU in waves of K leaves (b2_opd_plan_wave), one sub-tree after the other."""
         self.budget, self.gamma, self.terminal_reward = int(budget), float(gamma), float(terminal_reward)
         self.group, self.device, self.max_depth = group, device, max_depth
+        self.wave_width = int(wave_width)
 
     def _world(self):
         import torch.distributed as dist
@@ -371,7 +375,17 @@ class ShardedOPD(object):
         table = torch.full((max(len(subtrees), 1), 2), -np.inf, dtype=torch.float64, device=self.device)
         mine = [j for j in range(len(subtrees)) if j % world == rank]
         per_tree = max((self.budget - spent) // max(len(subtrees), 1), 5)
-        if mine:
+        if mine and self.wave_width > 0:
+            from rl_agents_b200.engine.opd import OPDWaveEngine
+            eng = OPDWaveEngine(_lib.ENV_HIGHWAY, 5, per_tree, g, self.wave_width, self.terminal_reward, device=self.device)
+            for j in mine:
+                node = top[subtrees[j]]
+                eng.plan(torch.tensor(node["words"], dtype=torch.int32, device=self.device))
+                eng.finish()
+                scale = g ** node["depth"]
+                table[j, 0] = node["lower"] + scale * float(eng.lower[0, 0].item())
+                table[j, 1] = node["lower"] + scale * float(eng.upper[0, 0].item())
+        elif mine:
             eng = OPDEngine(_lib.ENV_HIGHWAY, len(mine), 5, per_tree, g, self.terminal_reward, device=self.device,
                             keys_in_smem=True)
             eng.plan(torch.tensor(np.stack([top[subtrees[j]]["words"] for j in mine]), dtype=torch.int32,
