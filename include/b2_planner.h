@@ -125,7 +125,7 @@ typedef struct b2_vi_p2p {
     int32_t* viol_local;             /* [iterations] this rank's own counters (local scratch, zeroed)            */
     uint32_t* done;                  /* [iterations] retired-CTA counters (local scratch, zeroed)                */
     int32_t* status;                 /* [1] local scratch, zeroed: set to 1 when a peer's flag did not arrive within
-                                        ~4 s (the sweep then proceeds on stale data instead of hanging the GPU)    */
+                                        ~1 s (the sweep then proceeds on stale data instead of hanging the GPU)    */
 } b2_vi_p2p;
 
 /* Sweep `sweep_index` of the slab [row_begin, row_end): reads v[sweep&1][rank] and q_old, writes q_new and

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256) vi_sweep_row_p2p_kernel(P2PSweep g) {
             const int32_t* f = g.x.flags[rank] + tid;
             const long long t0 = clock64();
             while (ld_acquire_sys(f) < k) {
-                if (clock64() - t0 > 8000000000ll) { atomicExch(g.x.status, 1); break; }
+                if (*(volatile int32_t*)g.x.status != 0) break;            // a wait already timed out: do not wait again
+                if (clock64() - t0 > 2000000000ll) { atomicExch(g.x.status, 1); break; }
             }
         }
         __syncthreads();
