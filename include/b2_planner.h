@@ -58,6 +58,11 @@ typedef struct b2_finite_mdp {
 int b2_highway_step(int32_t* states, const int32_t* actions, float* reward, int32_t* flags,
                     int32_t* avail_mask, int32_t n_envs, void* stream);
 
+/* Self-test (tests/test_gpu_engines.py): the HighwayLite kernel divides by two constants of the spec with a
+ * 3-instruction sequence instead of the full IEEE division; this compares both, exhaustively over every fp32
+ * mantissa, both signs and exponents -60..60, and writes the number of differing results (must be 0). */
+int b2_selftest_const_division(unsigned long long* mismatches_dev, void* stream);
+
 /* ------------------------------------------------------------------------
  * Value iteration -- rl_agents/agents/dynamic_programming/value_iteration.py
  * ---------------------------------------------------------------------- */

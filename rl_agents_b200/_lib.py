@@ -107,6 +107,7 @@ EXPORTS = {
     "b2_last_error": (ctypes.c_char_p, []),
     "b2_version": (c_int, []),
     "b2_device_info": (c_int, [ctypes.POINTER(c_int)] * 3 + [ctypes.c_char_p, c_int]),
+    "b2_selftest_const_division": (c_int, [c_void_p, c_void_p]),
     "b2_highway_step": (c_int, [c_void_p] * 5 + [c_int32, c_void_p]),
     "b2_vi_sweep": (c_int, [ctypes.POINTER(VIProblem)] + [c_void_p] * 5 + [c_int32, c_void_p]),
     "b2_vi_solve": (c_int, [ctypes.POINTER(VIProblem)] + [c_void_p] * 5 + [c_int32, c_void_p]),

@@ -544,6 +544,22 @@ __global__ void __launch_bounds__(128) highway_step_kernel(int32_t* states, cons
     }
 }
 
+// Exhaustive check of hw::div_const against the IEEE division for the two constant divisors of the spec:
+// every fp32 mantissa, both signs, exponents -60 .. +60 (quotients stay normal).  Counts mismatching bit patterns.
+__global__ void const_division_selftest_kernel(unsigned long long* mismatches) {
+    const unsigned m = blockIdx.x * blockDim.x + threadIdx.x;       // mantissa, 2^23 threads
+    unsigned long long bad = 0;
+    for (int e = 127 - 60; e <= 127 + 60; e += 3) {
+        for (unsigned sgn = 0; sgn < 2; ++sgn) {
+            const float x = __uint_as_float((sgn << 31) | ((unsigned)e << 23) | m);
+            const float a = x / hw::TWO_SQRT_AB, b = hw::div_const(x, hw::TWO_SQRT_AB, hw::RCP_TWO_SQRT_AB);
+            const float c = x / hw::HALF_LENGTH, d = hw::div_const(x, hw::HALF_LENGTH, hw::RCP_HALF_LENGTH);
+            bad += (__float_as_uint(a) != __float_as_uint(b)) + (__float_as_uint(c) != __float_as_uint(d));
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 static int make_layout(const b2_opd_config* cfg, LevelLayout* lay, int smem_budget_doubles) {
     int n = cfg->node_capacity, l = 0;
     lay->n_levels = 0;
@@ -634,6 +650,14 @@ extern "C" int b2_opd_plan(const b2_opd_config* cfg, const int32_t* root_states,
         set_error("unknown env_kind %d", cfg->env_kind);
         return B2_ERR_INVALID;
     }
+    B2_CUDA_CHECK(cudaGetLastError());
+    return B2_OK;
+}
+
+extern "C" int b2_selftest_const_division(unsigned long long* mismatches_dev, void* stream) {
+    B2_REQUIRE(mismatches_dev, "null pointer");
+    B2_CUDA_CHECK(cudaMemsetAsync(mismatches_dev, 0, 8, (cudaStream_t)stream));
+    const_division_selftest_kernel<<<(1u << 23) / 256, 256, 0, (cudaStream_t)stream>>>(mismatches_dev);
     B2_CUDA_CHECK(cudaGetLastError());
     return B2_OK;
 }

@@ -654,3 +654,14 @@ def test_mcts_highway_c3_full_size_vs_c_oracle():
             assert np.array_equal(np.asarray(d[k], dtype=np.int64), t[k].astype(np.int64)), (i, k)
         assert np.array_equal(d["value"], t["value"]) and np.array_equal(d["prior"], t["prior"])
         assert rng_words[i].tolist() == w.tolist()
+
+
+def test_constant_divisor_division_is_ieee_exact_exhaustively():
+    """hw::div_const (3 instructions) against the IEEE division for the spec's two constant divisors: every
+    mantissa, both signs, 41 exponents -- on the device itself."""
+    import torch
+    from rl_agents_b200 import _lib
+    lib = _lib.load()
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(lib.b2_selftest_const_division(_lib.ptr(out), _lib.current_stream()))
+    assert int(out.item()) == 0
