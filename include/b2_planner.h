@@ -211,6 +211,7 @@ int b2_opd_plan(const b2_opd_config* cfg, const int32_t* root_states, const b2_o
  * (deterministic.py:106-122); for any width the result is bit-identical with the
  * specification oracle/planners.py::opd_plan_wavefront.
  * ---------------------------------------------------------------------- */
+#define B2_MAX_MODELS 8
 typedef struct b2_opd_wave_config {
     int32_t env_kind;       /* B2_ENV_*                                      */
     int32_t n_actions;      /* action_space.n (:118)                         */
@@ -219,11 +220,16 @@ typedef struct b2_opd_wave_config {
     int32_t plan_capacity;
     int32_t width;          /* leaves expanded per wave (>= 1)               */
     int32_t max_ctas;       /* 0: one CTA per SM                             */
-    int32_t reserved;
+    int32_t n_models;       /* 0: plain OPD.  M >= 1: DROP, the joint env of M models (rl_agents/agents/robust/
+                               robust.py:9-47): root_state / tree.state hold M states per node ([M] ids or
+                               [M,136] words), children follow the union of the models' available actions in
+                               ascending order, a node's bounds are the minima over the models of the per-model
+                               path bounds (deterministic.py:52-59 with vector rewards)            */
     const double* gamma_pow;      /* [n_expansions+2] gamma**d               */
     const double* gamma_pow_div;  /* [n_expansions+2] gamma**d / (1 - gamma) */
     const double* terminal_bonus; /* [n_expansions+2] terminal_reward * gamma**d / (1 - gamma) (:60-63) */
     b2_finite_mdp mdp;
+    b2_finite_mdp model_mdps[8];  /* env_kind FINITE and n_models > 0: one deterministic MDP per model */
 } b2_opd_wave_config;
 
 int64_t b2_opd_wave_workspace_bytes(const b2_opd_wave_config* cfg);

@@ -171,6 +171,67 @@ def opd_plan_wavefront(env, budget, gamma, width, terminal_reward=0.0, np_random
     return greedy_plan(t, t.lower, np_random), t
 
 
+def robust_plan(envs, budget, gamma, terminal_reward=0.0, np_random=None, width=1):
+    """DiscreteRobustPlanner.plan (rl_agents/agents/robust/robust.py:28-47, DROP) on the joint env of M models
+    (JointEnv, robust.py:9-26).  Every node carries one value_lower / value_upper PER MODEL along its own
+    path (deterministic.py:52-59: vector rewards and terminals); a leaf's bounds are the minima over the
+    models (RobustNode, robust.py:40-47), the frontier arg-max and the backups work on those minima
+    (deterministic.py:74-79 via get_value_*_bound).  Children follow JointEnv.get_available_actions: the
+    set union of the models' available actions, i.e. ascending action ids.  width > 1: the device's
+    wavefront (see opd_plan_wavefront); width = 1 is the reference's algorithm.  Returns (plan, tree);
+    tree.lower / tree.upper are the robust (min over models) bounds, tree.lowerv the per-model path sums."""
+    M = len(envs)
+    n_actions = envs[0].action_space.n
+    t = Tree()
+    t.parent, t.action, t.depth, t.count, t.first_child, t.n_children = [-1], [-1], [0], [1], [-1], [0]
+    t.lower, t.upper, t.lowerv, t.done = [0.0], [0.0], [[0.0] * M], [[False] * M]
+    states = [list(envs)]
+    leaves = {0}
+    remaining = int(budget) // n_actions
+    t.waves = []
+    while remaining > 0:
+        k = min(int(width), remaining, len(leaves))
+        chosen = sorted(sorted(leaves, key=lambda i: (-t.upper[i], i))[:k])
+        t.waves.append(chosen)
+        for best in chosen:
+            leaves.remove(best)
+            actions = sorted(set().union(*[_available_actions(s) for s in states[best]]))
+            t.first_child[best], t.n_children[best] = len(t.parent), len(actions)
+            d = t.depth[best] + 1
+            for a in actions:
+                models = [copy.deepcopy(s) for s in states[best]]
+                lov, upv, dn = [], [], []
+                for m, st in enumerate(models):
+                    _, reward, done, _, _ = st.step(a)
+                    if not (0 <= reward <= 1):
+                        raise ValueError("This planner assumes that all rewards are normalized in [0, 1]")
+                    lo = t.lowerv[best][m] + (gamma ** (d - 1)) * reward
+                    up = lo + (gamma ** d) / (1 - gamma)
+                    if done:
+                        lo = up = lo + terminal_reward * (gamma ** d) / (1 - gamma)
+                    lov.append(lo); upv.append(up); dn.append(bool(done))
+                c = len(t.parent)
+                t.parent.append(best); t.action.append(a); t.depth.append(d); t.count.append(1)
+                t.first_child.append(-1); t.n_children.append(0)
+                t.lowerv.append(lov); t.done.append(dn)
+                t.lower.append(min(lov)); t.upper.append(min(upv))
+                states.append(models)
+                leaves.add(c)
+            states[best] = None
+        remaining -= k
+    for c in range(len(t.parent) - 1, 0, -1):
+        n = c
+        while n >= 0:
+            t.count[n] += 1
+            n = t.parent[n]
+    for n in range(len(t.parent) - 1, -1, -1):
+        if t.n_children[n]:
+            t.lower[n] = max(t.lower[c] for c in t.children(n))
+            t.upper[n] = max(t.upper[c] for c in t.children(n))
+    t.n_leaves = len(leaves)
+    return greedy_plan(t, t.lower, np_random), t
+
+
 def greedy_plan(t, values, np_random):
     """AbstractPlanner.get_plan (abstract.py:143-156) with
     DeterministicNode.selection_rule (deterministic.py:21-26): arg-max of the

@@ -54,8 +54,9 @@ class OPDConfig(ctypes.Structure):
 class OPDWaveConfig(ctypes.Structure):
     _fields_ = [("env_kind", c_int32), ("n_actions", c_int32), ("n_expansions", c_int32),
                 ("node_capacity", c_int32), ("plan_capacity", c_int32), ("width", c_int32),
-                ("max_ctas", c_int32), ("reserved", c_int32), ("gamma_pow", c_void_p),
-                ("gamma_pow_div", c_void_p), ("terminal_bonus", c_void_p), ("mdp", FiniteMDP)]
+                ("max_ctas", c_int32), ("n_models", c_int32), ("gamma_pow", c_void_p),
+                ("gamma_pow_div", c_void_p), ("terminal_bonus", c_void_p), ("mdp", FiniteMDP),
+                ("model_mdps", FiniteMDP * 8)]
 
 
 class OPDTree(ctypes.Structure):

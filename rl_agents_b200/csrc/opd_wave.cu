@@ -58,6 +58,9 @@ struct Args {
     int32_t* exp_order;    // [n_expansions] expanded leaves, wave-major, id order inside a wave
     int32_t* wave_start;   // [n_expansions + 1]
     int32_t* work;         // [width * n_actions] leaf | action << 28 for every child of the current wave
+    double* lowerv;        // joint (robust) mode: [node_capacity, n_models] per-model value_lower along the node's path
+    double* wave_up;       // joint mode: [width * n_actions, n_models] per-model value_upper of the wave's children
+    int32_t* wave_flags;   // joint mode: done | avail << 8 | reward-out-of-range << 16, per (child, model)
     DistScratch* dscr;     // distributed selection (trees larger than one shared-memory tile)
     int2* cta_cnt;         // [grid] per-CTA (taken-by-threshold, equal-to-threshold) counts
     int8_t* plan;
@@ -164,11 +167,11 @@ __device__ int layout_wave(const Args& a, SelShared& sh, unsigned long long* ske
             int q = 0;
             for (int act_i = 0; act_i < MAX_BRANCH; ++act_i) {
                 int act;
-                if (a.cfg.env_kind == B2_ENV_HIGHWAY) {
+                if (a.cfg.env_kind == B2_ENV_HIGHWAY && a.cfg.n_models == 0) {
                     if (act_i >= 5) break;
                     const int order[5] = {hw::A_IDLE, hw::A_LEFT, hw::A_RIGHT, hw::A_FASTER, hw::A_SLOWER};
                     act = order[act_i];
-                } else {
+                } else {     // finite MDPs, and JointEnv.get_available_actions (robust.py:22-26): ascending ids
                     if (act_i >= a.cfg.n_actions) break;
                     act = act_i;
                 }
@@ -581,6 +584,57 @@ __device__ __forceinline__ void load_state_cg(const int32_t* w, int li, hw::Lane
     si = __ldcg(w + 8 * hw::V + 1);
 }
 
+// Joint (robust) mode, per (child, model): the model's own path bounds (deterministic.py:52-59 with vector
+// rewards / terminals); the node's bounds are their minima over the models (robust.py:40-47), taken by
+// finalize_joint_children once every model of the wave has been simulated.
+__device__ __forceinline__ void write_model_bounds(const Args& a, int task, int c, int leaf, int m, double r, bool done,
+                                                   int avail) {
+    const int M = a.cfg.n_models;
+    const int d = ld_cg(a.tree.depth + leaf) + 1;
+    double lo = ld_cg(a.lowerv + (int64_t)leaf * M + m) + a.cfg.gamma_pow[d - 1] * r;
+    double up = lo + a.cfg.gamma_pow_div[d];
+    if (done) {
+        lo = lo + a.cfg.terminal_bonus[d];
+        up = lo;
+    }
+    a.lowerv[(int64_t)c * M + m] = lo;
+    a.wave_up[task] = up;
+    a.wave_flags[task] = (done ? 1 : 0) | (avail << 8) | ((r >= 0.0 && r <= 1.0) ? 0 : 1 << 16);
+}
+
+__device__ __forceinline__ void finalize_joint_children(const Args& a, int total, int base, unsigned n_ctas) {
+    const int M = a.cfg.n_models;
+    const b2_opd_tree& tr = a.tree;
+    for (int w = blockIdx.x * THREADS + threadIdx.x; w < total; w += THREADS * (int)n_ctas) {
+        const int item = __ldcg(a.work + w);
+        const int leaf = item & 0x0fffffff, action = (item >> 28) & 7;
+        const int c = base + w;
+        const int d = ld_cg(tr.depth + leaf) + 1;
+        double lo = INFINITY, up = INFINITY;
+        int done_all = 1, avail = 0, bad = 0;
+        for (int m = 0; m < M; ++m) {
+            const double l2 = __ldcg(a.lowerv + (int64_t)c * M + m), u2 = __ldcg(a.wave_up + (int64_t)w * M + m);
+            const int f = __ldcg(a.wave_flags + (int64_t)w * M + m);
+            lo = l2 < lo ? l2 : lo;          // np.min over the models (robust.py:41-44)
+            up = u2 < up ? u2 : up;
+            done_all &= f & 1;
+            avail |= (f >> 8) & 0xff;
+            bad |= f >> 16;
+        }
+        tr.parent[c] = leaf;
+        tr.first_child[c] = -1;
+        tr.depth[c] = d;
+        tr.count[c] = 2;
+        tr.meta[c] = action | (done_all ? 1 << 16 : 0) | (avail << 24);
+        tr.reward[c] = 0.0;
+        tr.lower[c] = lo;
+        tr.upper[c] = up;
+        a.keys[c] = up;
+        if (bad) a.ctl->error = 1;
+        atomicMax(&a.ctl->max_depth, d);
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
     extern __shared__ unsigned long long skeys[];
     __shared__ SelShared sh;
@@ -594,12 +648,16 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
     if (blockIdx.x == 0) {
         // root: DeterministicNode.__init__ (:10-19)
         int avail = 0;
+        const int Mx = a.cfg.n_models > 0 ? a.cfg.n_models : 1;
         if (hwy) {
-            for (int i = tid; i < hw::WORDS; i += THREADS) tr.state[i] = a.root_state[i];
-            avail = hw::avail_mask(__int_as_float(a.root_state[hw::V]), a.root_state[8 * hw::V + 1]);
-        } else if (tid == 0) {
-            tr.state[0] = a.root_state[0];
+            for (int i = tid; i < Mx * hw::WORDS; i += THREADS) tr.state[i] = a.root_state[i];
+            for (int m = 0; m < Mx; ++m)      // JointEnv.get_available_actions: the union over the models
+                avail |= hw::avail_mask(__int_as_float(a.root_state[m * hw::WORDS + hw::V]),
+                                        a.root_state[m * hw::WORDS + 8 * hw::V + 1]);
+        } else if (tid < Mx) {
+            tr.state[tid] = a.root_state[tid];
         }
+        if (a.cfg.n_models > 0 && tid < a.cfg.n_models) a.lowerv[tid] = 0.0;
         if (tid == 0) {
             tr.parent[0] = -1; tr.first_child[0] = -1; tr.depth[0] = 0; tr.count[0] = 1;
             tr.meta[0] = 0xff | (avail << 24);
@@ -652,26 +710,46 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
         if (*(volatile int*)&ctl->stop) break;
         const int total = *(volatile int*)&ctl->wave_children;
         const int base = *(volatile int*)&ctl->wave_base;
+        const int M = a.cfg.n_models, Mx = M > 0 ? M : 1;
         if (hwy) {
-            // consecutive children go to different SMs first: a small wave runs one warp per SM
+            // one (child, model) per 16-lane group; consecutive tasks go to different SMs first: a small wave
+            // runs one warp per SM
             const int warp_global = (tid >> 5) * (int)n_ctas + (int)blockIdx.x;
             const int n_warps = WARPS * (int)n_ctas;
-            for (int w0 = 2 * warp_global; w0 < total; w0 += 2 * n_warps) {
-                const int w = w0 + ((tid >> 4) & 1);
-                const bool real = w < total;
-                const int item = __ldcg(a.work + (real ? w : w0));
+            const int n_tasks = total * Mx;
+            for (int w0 = 2 * warp_global; w0 < n_tasks; w0 += 2 * n_warps) {
+                const int task_raw = w0 + ((tid >> 4) & 1);
+                const bool real = task_raw < n_tasks;
+                const int task = real ? task_raw : w0;
+                const int w = task / Mx, m = task - w * Mx;
+                const int item = __ldcg(a.work + w);
                 const int leaf = item & 0x0fffffff, action = real ? (item >> 28) & 7 : hw::A_IDLE;
                 hw::Lane L;
                 int t, si;
-                load_state_cg(tr.state + (int64_t)leaf * hw::WORDS, li, L, t, si);
+                load_state_cg(tr.state + ((int64_t)leaf * Mx + m) * hw::WORDS, li, L, t, si);
                 bool term, trunc;
                 const float r = hw::step(L, li, t, si, action, term, trunc, 0xffffffffu, hw_scratch[tid >> 4]);
                 const float ego_y = __shfl_sync(0xffffffffu, L.y, 0, 16);
                 if (real) {
                     const int c = base + w;
-                    hw::store_state(tr.state + (int64_t)c * hw::WORDS, li, L, t, si);
-                    if (li == 0) write_child(a, c, leaf, action, (double)r, term, hw::avail_mask(ego_y, si));
+                    hw::store_state(tr.state + ((int64_t)c * Mx + m) * hw::WORDS, li, L, t, si);
+                    if (li == 0) {
+                        if (M == 0) write_child(a, c, leaf, action, (double)r, term, hw::avail_mask(ego_y, si));
+                        else write_model_bounds(a, task, c, leaf, m, (double)r, term, hw::avail_mask(ego_y, si));
+                    }
                 }
+            }
+        } else if (M > 0) {
+            for (int task = blockIdx.x * THREADS + tid; task < total * M; task += THREADS * (int)n_ctas) {
+                const int w = task / M, m = task - w * M;
+                const b2_finite_mdp& mm = a.cfg.model_mdps[m];
+                const int item = __ldcg(a.work + w);
+                const int leaf = item & 0x0fffffff, action = (item >> 28) & 7;
+                const int s = ld_cg(tr.state + (int64_t)leaf * M + m);
+                const int c = base + w;
+                tr.state[(int64_t)c * M + m] = mm.transition[(int64_t)s * mm.n_actions + action];
+                write_model_bounds(a, task, c, leaf, m, mm.reward[(int64_t)s * mm.n_actions + action],
+                                   mm.terminal[s] != 0, 0);
             }
         } else {
             const b2_finite_mdp& m = a.cfg.mdp;
@@ -686,6 +764,10 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
             }
         }
         lap(4);
+        if (M > 0) {        // the children's robust bounds need every model's result
+            grid_barrier(ctl, n_ctas);
+            finalize_joint_children(a, total, base, n_ctas);
+        }
         grid_barrier(ctl, n_ctas);
         lap(5);
         if (*(volatile int*)&ctl->error) break;
@@ -749,7 +831,7 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
 static int64_t align_up(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 struct Layout {
-    int64_t ctl, keys, exp_order, wave_start, work, dscr, cta_cnt, total;
+    int64_t ctl, keys, exp_order, wave_start, work, lowerv, wave_up, wave_flags, dscr, cta_cnt, total;
 };
 
 static Layout make_layout(const b2_opd_wave_config* c) {
@@ -759,7 +841,11 @@ static Layout make_layout(const b2_opd_wave_config* c) {
     l.exp_order = l.keys + align_up((int64_t)c->node_capacity * 8);
     l.wave_start = l.exp_order + align_up((int64_t)c->n_expansions * 4 + 4);
     l.work = l.wave_start + align_up(((int64_t)c->n_expansions + 2) * 4);
-    l.dscr = l.work + align_up((int64_t)c->width * c->n_actions * 4 + 4);
+    const int64_t M = c->n_models > 0 ? c->n_models : 0;
+    l.lowerv = l.work + align_up((int64_t)c->width * c->n_actions * 4 + 4);
+    l.wave_up = l.lowerv + align_up((int64_t)c->node_capacity * M * 8);
+    l.wave_flags = l.wave_up + align_up((int64_t)c->width * c->n_actions * M * 8);
+    l.dscr = l.wave_flags + align_up((int64_t)c->width * c->n_actions * M * 4);
     l.cta_cnt = l.dscr + align_up(sizeof(DistScratch));
     l.total = l.cta_cnt + align_up(1024 * sizeof(int2));
     return l;
@@ -784,7 +870,13 @@ extern "C" int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* ro
     B2_REQUIRE(cfg->node_capacity < (1 << 28), "node_capacity must be < 2^28");
     B2_REQUIRE(cfg->plan_capacity >= 1, "plan_capacity too small");
     B2_REQUIRE(cfg->gamma_pow && cfg->gamma_pow_div && cfg->terminal_bonus, "gamma tables missing");
-    if (cfg->env_kind == B2_ENV_FINITE) {
+    B2_REQUIRE(cfg->n_models >= 0 && cfg->n_models <= B2_MAX_MODELS, "n_models must be in 0..8");
+    if (cfg->env_kind == B2_ENV_FINITE && cfg->n_models > 0) {
+        for (int m = 0; m < cfg->n_models; ++m) {
+            const b2_finite_mdp& mm = cfg->model_mdps[m];
+            B2_REQUIRE(mm.transition && mm.reward && mm.terminal && mm.n_actions == cfg->n_actions, "model MDP tables missing");
+        }
+    } else if (cfg->env_kind == B2_ENV_FINITE) {
         B2_REQUIRE(cfg->mdp.transition && cfg->mdp.reward && cfg->mdp.terminal, "finite MDP tables missing");
         B2_REQUIRE(cfg->mdp.n_actions == cfg->n_actions, "mdp.n_actions != n_actions");
     } else if (cfg->env_kind == B2_ENV_HIGHWAY) {
@@ -803,6 +895,9 @@ extern "C" int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* ro
     a.exp_order = (int32_t*)(ws + l.exp_order);
     a.wave_start = (int32_t*)(ws + l.wave_start);
     a.work = (int32_t*)(ws + l.work);
+    a.lowerv = (double*)(ws + l.lowerv);
+    a.wave_up = (double*)(ws + l.wave_up);
+    a.wave_flags = (int32_t*)(ws + l.wave_flags);
     a.dscr = (wave::DistScratch*)(ws + l.dscr);
     a.cta_cnt = (int2*)(ws + l.cta_cnt);
     a.plan = plan; a.result = result;

@@ -118,13 +118,34 @@ class OPDWaveEngine(OPDEngine):
     n_trees = 1."""
 
     def __init__(self, env_kind, n_actions, budget, gamma, width, terminal_reward=0.0, mdp=None, device="cuda",
-                 max_ctas=0):
-        super(OPDWaveEngine, self).__init__(env_kind, 1, n_actions, budget, gamma, terminal_reward, mdp, device)
+                 max_ctas=0, n_models=0, model_mdps=None):
+        """n_models = M >= 1: DROP (DiscreteRobustPlanner, rl_agents/agents/robust/robust.py) -- the joint env of M
+        models; `model_mdps`: the M finite MDPs (env_kind FINITE), root states [M] ids or [M, 136] words."""
+        first = model_mdps[0] if (model_mdps and env_kind == _lib.ENV_FINITE) else mdp
+        super(OPDWaveEngine, self).__init__(env_kind, 1, n_actions, budget, gamma, terminal_reward, first, device)
         self.width = int(width)
+        self.n_models = int(n_models)
+        torch = self.torch
+        self.model_tables = []
+        if self.n_models > 0:
+            if self.n_models > 8:
+                raise ValueError("at most 8 models")
+            if env_kind == _lib.ENV_FINITE:
+                if not model_mdps or len(model_mdps) != self.n_models:
+                    raise ValueError("model_mdps must list one finite MDP per model")
+                self.model_tables = [FiniteTables(m, self.device) for m in model_mdps]
+                self.state = torch.empty((1, self.capacity, self.n_models), dtype=torch.int32, device=self.device)
+            else:
+                self.state = torch.empty((1, self.capacity, self.n_models, _lib.HW_STATE_WORDS), dtype=torch.int32,
+                                         device=self.device)
+            self.tree = _lib.OPDTree(*[t.data_ptr() for t in (self.parent, self.first_child, self.depth, self.count,
+                                                              self.meta, self.reward, self.lower, self.upper, self.state)])
         self.wcfg = _lib.OPDWaveConfig(env_kind, self.n_actions, self.n_expansions, self.capacity, self.plan_capacity,
-                                       self.width, int(max_ctas), 0, self.gamma_pow.data_ptr(),
+                                       self.width, int(max_ctas), self.n_models, self.gamma_pow.data_ptr(),
                                        self.gamma_pow_div.data_ptr(), self.terminal_bonus.data_ptr(),
                                        self.tables.struct() if self.tables else _lib.FiniteMDP())
+        for m, tab in enumerate(self.model_tables):
+            self.wcfg.model_mdps[m] = tab.struct()
         ws = self.lib.b2_opd_wave_workspace_bytes(self.wcfg)
         if ws < 0:
             raise _lib.B2Error("unsupported wavefront OPD configuration")

@@ -95,6 +95,23 @@ class HighwayLiteEnv(object):
     def get_available_actions(self):
         return available_actions(self.words)
 
+    def assume_traffic(self, args):
+        """Model variant for robust planning (`"models": [[{"method": "assume_traffic", "args": {...}}], ...]`):
+        a planning copy in which the other vehicles' target speeds are shifted by `target_speed_offset` m/s
+        and / or the vehicle in slot `cut_in_slot` intends to move `cut_in_direction` lanes (-1 left, +1 right)."""
+        env = copy.deepcopy(self)
+        f = env.words[:96].view(np.float32)
+        present = (env.words[112:128] & 1) != 0
+        off = np.float32(args.get("target_speed_offset", 0.0))
+        for k in range(1, V_SLOTS):
+            if present[k]:
+                f[4 * 16 + k] = np.float32(f[4 * 16 + k] + off)
+        slot = args.get("cut_in_slot")
+        if slot is not None and 0 < int(slot) < V_SLOTS and present[int(slot)]:
+            env.words[96 + int(slot)] = int(np.clip(env.words[96 + int(slot)] + int(args.get("cut_in_direction", -1)),
+                                                    0, N_LANES - 1))
+        return env
+
     def observation(self):
         f = self.words[:64].view(np.float32).reshape(4, V_SLOTS)
         present = (self.words[112:128] & 1).astype(np.float32)

@@ -217,6 +217,38 @@ def main():
     mc["large1_terminal_b600_g0.9"] = run_mcts(finite(T, R, termx), {"budget": 600, "gamma": 0.9}, seed=1)
     out["mcts"] = mc
 
+    # ---------------- DROP: DiscreteRobustPlanner on the joint env of M models (robust.py:9-47) ----------------
+    # the reference's JointEnv.step returns the legacy 4-tuple while DeterministicNode.expand unpacks five values
+    # (deterministic.py:41): the shim below only re-packs the tuple, like the OLOP legacy shim does the other way
+    from rl_agents.agents.robust import robust as ref_robust
+
+    class JointEnv5(ref_robust.JointEnv):
+        def step(self, action):
+            transitions = [state.step(action) for state in self.joint_state]
+            observations, rewards, terminals, truncated, info = zip(*transitions)
+            return observations, np.array(rewards), np.array(terminals), np.array(truncated), info
+
+    drop = {}
+    for key, (names, bud, gam, tr_) in {"large12_b300_g0.85": (("large1", "large2"), 300, 0.85, 0.0),
+                                         "large1x3_terminal_b400_g0.8": (("large1", "large1t", "large2"), 400, 0.8, 0.3)}.items():
+        def model(nm):
+            if nm == "large1":
+                return finite()
+            if nm == "large1t":
+                return finite(T, R, termx)
+            return finite(T2, R2, term2)
+        del CREATED[:]
+        agent = ref_robust.DiscreteRobustPlannerAgent(finite(), {"budget": bud, "gamma": gam, "terminal_reward": tr_})
+        agent.seed(0)
+        agent.env = JointEnv5([model(nm) for nm in names])
+        plan = ref_det.DeterministicPlannerAgent.plan(agent, None)       # skip robust.py:66-67 (env preprocessing)
+        for n in CREATED:
+            n.lower, n.upper = float(np.min(n.value_lower)), float(np.min(n.value_upper))
+        tree = dump_tree(["lower", "upper"], agent.planner.root)
+        drop[key] = {"models": list(names), "budget": bud, "gamma": gam, "terminal_reward": tr_,
+                     "plan": [int(a) for a in plan], "tree": summarize(tree, True)}
+    out["drop"] = drop
+
     # ---------------- MCTS policies other than random_available (mcts.py:34-97) ----------------
     pol = {}
     pref_cfg = {"budget": 400, "gamma": 0.8,

@@ -204,3 +204,79 @@ def test_wave_finite_large_tree_distributed_selection_with_ties():
         plan, tree = planners.opd_plan_wavefront(oenvs.FiniteMDPLite(T, R, term), 120000, 0.9, width, np_random=np_random(0))
         res = check(eng, plan, tree)
         assert int(res[0, 7]) == len(tree.waves)
+
+
+# ------------------------------------------------------------------ DROP (robust.py) ----
+def _models(names):
+    from rl_agents_b200.envs.finite_mdp import FiniteMDP
+    termx = M["large1_term"].copy()
+    termx[[3, 17, 66, 91]] = True
+    table = {"large1": ("large1", M["large1_term"]), "large1t": ("large1", termx), "large2": ("large2", M["large2_term"])}
+    prod = [FiniteMDP("deterministic", M[table[n][0] + "_T"], M[table[n][0] + "_R"], table[n][1]) for n in names]
+    orac = [oenvs.FiniteMDPLite(M[table[n][0] + "_T"], M[table[n][0] + "_R"], table[n][1]) for n in names]
+    return prod, orac
+
+
+def test_drop_finite_matches_the_reference_goldens():
+    """DiscreteRobustPlanner (robust.py:28-47) on joint envs of 2 and 3 finite-MDP models: plan, node order,
+    counts and robust bounds equal the UNMODIFIED reference's (tests/golden, 'drop')."""
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    from tests.util import load_golden
+    G = load_golden("golden_finite.json")
+    for key, g in G["drop"].items():
+        prod, _ = _models(g["models"])
+        eng = OPDWaveEngine(_lib.ENV_FINITE, 5, g["budget"], g["gamma"], 1, terminal_reward=g["terminal_reward"],
+                            n_models=len(prod), model_mdps=prod)
+        eng.plan(torch.zeros(len(prod), dtype=torch.int32, device="cuda"))
+        plans, _ = eng.finish([np_random(0)])
+        d = eng.tree_dict(0)
+        t = g["tree"]
+        assert plans[0] == g["plan"], key
+        assert d["parent"].tolist() == t["parent"] and d["action"].tolist() == t["action"]
+        assert d["count"].tolist() == t["count"]
+        assert np.array_equal(d["lower"], np.array(t["lower"])) and np.array_equal(d["upper"], np.array(t["upper"]))
+
+
+@pytest.mark.parametrize("width", [1, 8])
+def test_drop_highway_matches_the_oracle(width):
+    """Joint env of three HighwayLite models (different assumed traffic) against oracle.planners.robust_plan
+    (itself pinned to the reference on the finite goldens)."""
+    import torch
+    from rl_agents_b200 import _lib
+    from rl_agents_b200.engine.opd import OPDWaveEngine
+    states = []
+    for off in (0.0, -3.0, 2.0):
+        st = oenvs.make_highway_state(5)
+        st.tgt_speed[1:] = (st.tgt_speed[1:] + np.float32(off)).astype(np.float32)
+        states.append(st)
+    eng = OPDWaveEngine(_lib.ENV_HIGHWAY, 5, 300, 0.8, width, n_models=3)
+    eng.plan(torch.tensor(np.stack([s.pack() for s in states]), dtype=torch.int32, device="cuda"))
+    plans, _ = eng.finish([np_random(0)])
+    plan, t = planners.robust_plan([oenvs.HighwayLite(s.copy()) for s in states], 300, 0.8, np_random=np_random(0),
+                                   width=width)
+    d = eng.tree_dict(0)
+    assert plans[0] == plan
+    assert d["parent"].tolist() == t.parent and d["action"].tolist() == t.action and d["count"].tolist() == t.count
+    assert np.array_equal(d["lower"], np.array(t.lower)) and np.array_equal(d["upper"], np.array(t.upper))
+
+
+def test_drop_agent_plugin_surface():
+    """DiscreteRobustPlannerAgent: `models` = one preprocessor chain per model, like the reference's configs."""
+    from rl_agents_b200.agents.robust.robust import DiscreteRobustPlannerAgent
+    from rl_agents_b200.envs import HighwayLiteEnv
+    env = HighwayLiteEnv(seed=5)
+    models = [[{"method": "simplify"}],
+              [{"method": "assume_traffic", "args": {"target_speed_offset": -3.0}}],
+              [{"method": "assume_traffic", "args": {"target_speed_offset": 2.0}}]]
+    agent = DiscreteRobustPlannerAgent(env, {"budget": 300, "gamma": 0.8, "models": models})
+    agent.seed(0)
+    states = []
+    for off in (0.0, -3.0, 2.0):
+        st = oenvs.make_highway_state(5)
+        st.tgt_speed[1:] = (st.tgt_speed[1:] + np.float32(off)).astype(np.float32)
+        states.append(oenvs.HighwayLite(st))
+    plan, _ = planners.robust_plan(states, 300, 0.8, np_random=np_random(0))
+    assert agent.plan(env.observation()) == plan
+    assert agent.config["models"] == models

@@ -293,3 +293,17 @@ def test_preference_tables_follow_numpy():
     c /= c[-1]
     assert np.array_equal(cdf[4, 3, :4], c)
     assert np.array_equal(prior[3, 0, :3], np.ones(3) / 3)
+
+
+def test_drop_oracle_matches_the_reference_goldens():
+    """oracle.planners.robust_plan against DiscreteRobustPlanner of the unmodified reference (joint env of 2 / 3
+    finite-MDP models, one with terminal states and a terminal reward)."""
+    termx = M["large1_term"].copy()
+    termx[[3, 17, 66, 91]] = True
+    table = {"large1": ("large1", M["large1_term"]), "large1t": ("large1", termx), "large2": ("large2", M["large2_term"])}
+    for key, g in G["drop"].items():
+        models = [envs.FiniteMDPLite(M[table[n][0] + "_T"], M[table[n][0] + "_R"], table[n][1]) for n in g["models"]]
+        plan, t = planners.robust_plan(models, g["budget"], g["gamma"], g["terminal_reward"], np_random(0))
+        assert plan == g["plan"], key
+        assert t.parent == g["tree"]["parent"] and t.action == g["tree"]["action"] and t.count == g["tree"]["count"]
+        assert t.lower == g["tree"]["lower"] and t.upper == g["tree"]["upper"]
