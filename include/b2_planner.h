@@ -38,8 +38,11 @@ int b2_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int 
 #define B2_ENV_FINITE 0   /* deterministic finite MDP tables               */
 #define B2_ENV_HIGHWAY 1  /* HighwayLite, docs/HIGHWAY_LITE_SPEC.md         */
 
-#define B2_HW_STATE_WORDS 136 /* 32-bit words of one HighwayLite state      */
+#define B2_ENV_INTERSECTION 2 /* IntersectionLite, docs/INTERSECTION_LITE_SPEC.md (wavefront OPD + b2_intersection_step) */
+
+#define B2_HW_STATE_WORDS 136 /* 32-bit words of one HighwayLite / IntersectionLite state */
 #define B2_HW_ACTIONS 5
+#define B2_IL_ACTIONS 3
 
 typedef struct b2_finite_mdp {
     int32_t n_states;
@@ -57,6 +60,11 @@ typedef struct b2_finite_mdp {
  * bitmask of get_available_actions() in the NEW state. */
 int b2_highway_step(int32_t* states, const int32_t* actions, float* reward, int32_t* flags,
                     int32_t* avail_mask, int32_t n_envs, void* stream);
+
+/* The same for IntersectionLite (BASELINE config C5's env model): 3 actions (0 SLOWER, 1 IDLE, 2 FASTER),
+ * states [n_envs, 136] words, avail_mask in the NEW state. */
+int b2_intersection_step(int32_t* states, const int32_t* actions, float* reward, int32_t* flags,
+                         int32_t* avail_mask, int32_t n_envs, void* stream);
 
 /* Self-test (tests/test_gpu_engines.py): the HighwayLite kernel divides by two constants of the spec with a
  * 3-instruction sequence instead of the full IEEE division; this compares both, exhaustively over every fp32

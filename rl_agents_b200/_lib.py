@@ -14,7 +14,7 @@ c_void_p, c_int, c_int32, c_int64, c_double = (ctypes.c_void_p, ctypes.c_int, ct
 
 HW_STATE_WORDS = 136
 HW_ACTIONS = 5
-ENV_FINITE, ENV_HIGHWAY = 0, 1
+ENV_FINITE, ENV_HIGHWAY, ENV_INTERSECTION = 0, 1, 2
 VI_DETERMINISTIC, VI_STOCHASTIC, VI_SPARSE = 0, 1, 2
 OPD_RESULT_WORDS = 16
 MCTS_RESULT_WORDS = 8
@@ -108,6 +108,7 @@ EXPORTS = {
     "b2_last_error": (ctypes.c_char_p, []),
     "b2_version": (c_int, []),
     "b2_device_info": (c_int, [ctypes.POINTER(c_int)] * 3 + [ctypes.c_char_p, c_int]),
+    "b2_intersection_step": (c_int, [c_void_p] * 5 + [c_int32, c_void_p]),
     "b2_selftest_const_division": (c_int, [c_void_p, c_void_p]),
     "b2_highway_step": (c_int, [c_void_p] * 5 + [c_int32, c_void_p]),
     "b2_vi_sweep": (c_int, [ctypes.POINTER(VIProblem)] + [c_void_p] * 5 + [c_int32, c_void_p]),

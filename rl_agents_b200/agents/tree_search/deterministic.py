@@ -4,6 +4,7 @@ rl_agents.agents.tree_search.deterministic.DeterministicPlannerAgent
 plan()/act() results on identical seeds."""
 from rl_agents_b200.agents.common.abstract import register_with_reference
 from rl_agents_b200.agents.tree_search.abstract import AbstractPlanner, AbstractTreeSearchAgent
+from rl_agents_b200 import _lib
 from rl_agents_b200.envs.adapters import describe, mdp_fingerprint
 
 
@@ -20,6 +21,8 @@ class OptimisticDeterministicPlanner(AbstractPlanner):
         (b2_opd_plan_wave; K = 1 is again the strict order) -- 30-60x lower latency at K = 64..128."""
         from rl_agents_b200.engine.opd import OPDEngine, OPDWaveEngine
         width = int(self.config.get("wavefront", 0) or 0)
+        if d.kind == _lib.ENV_INTERSECTION:
+            width = max(width, 1)          # IntersectionLite lives in the wavefront kernel (width 1 = strict order)
         key = (d.kind, d.n_actions, self.config["budget"], self.config["gamma"],
                self.config.get("terminal_reward", 0), width, mdp_fingerprint(d.mdp))
         if key != self._engine_key:

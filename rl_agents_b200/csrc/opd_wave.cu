@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "highway_lite.cuh"
+#include "intersection_lite.cuh"
 
 namespace b2 {
 namespace wave {
@@ -152,7 +153,7 @@ __device__ int layout_wave(const Args& a, SelShared& sh, unsigned long long* ske
         if (j < k) {
             leaf = __ldcg(sel + j);
             meta = __ldcg(a.tree.meta + leaf);
-            mask = a.cfg.env_kind == B2_ENV_HIGHWAY ? (meta >> 24) & 0x1f : (1 << a.cfg.n_actions) - 1;
+            mask = a.cfg.env_kind != B2_ENV_FINITE ? (meta >> 24) & 0x1f : (1 << a.cfg.n_actions) - 1;
             n = __popc(mask);
             term += (meta >> 16) & 1;
         }
@@ -170,6 +171,10 @@ __device__ int layout_wave(const Args& a, SelShared& sh, unsigned long long* ske
                 if (a.cfg.env_kind == B2_ENV_HIGHWAY && a.cfg.n_models == 0) {
                     if (act_i >= 5) break;
                     const int order[5] = {hw::A_IDLE, hw::A_LEFT, hw::A_RIGHT, hw::A_FASTER, hw::A_SLOWER};
+                    act = order[act_i];
+                } else if (a.cfg.env_kind == B2_ENV_INTERSECTION) {
+                    if (act_i >= 3) break;
+                    const int order[3] = {il::A_IDLE, il::A_FASTER, il::A_SLOWER};
                     act = order[act_i];
                 } else {     // finite MDPs, and JointEnv.get_available_actions (robust.py:22-26): ascending ids
                     if (act_i >= a.cfg.n_actions) break;
@@ -649,7 +654,10 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
         // root: DeterministicNode.__init__ (:10-19)
         int avail = 0;
         const int Mx = a.cfg.n_models > 0 ? a.cfg.n_models : 1;
-        if (hwy) {
+        if (a.cfg.env_kind == B2_ENV_INTERSECTION) {
+            for (int i = tid; i < il::WORDS; i += THREADS) tr.state[i] = a.root_state[i];
+            avail = il::avail_mask(a.root_state[129]);
+        } else if (hwy) {
             for (int i = tid; i < Mx * hw::WORDS; i += THREADS) tr.state[i] = a.root_state[i];
             for (int m = 0; m < Mx; ++m)      // JointEnv.get_available_actions: the union over the models
                 avail |= hw::avail_mask(__int_as_float(a.root_state[m * hw::WORDS + hw::V]),
@@ -737,6 +745,26 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
                         if (M == 0) write_child(a, c, leaf, action, (double)r, term, hw::avail_mask(ego_y, si));
                         else write_model_bounds(a, task, c, leaf, m, (double)r, term, hw::avail_mask(ego_y, si));
                     }
+                }
+            }
+        } else if (a.cfg.env_kind == B2_ENV_INTERSECTION) {
+            const int warp_global = (tid >> 5) * (int)n_ctas + (int)blockIdx.x;
+            const int n_warps = WARPS * (int)n_ctas;
+            for (int w0 = 2 * warp_global; w0 < total; w0 += 2 * n_warps) {
+                const int w_raw = w0 + ((tid >> 4) & 1);
+                const bool real = w_raw < total;
+                const int w = real ? w_raw : w0;
+                const int item = __ldcg(a.work + w);
+                const int leaf = item & 0x0fffffff, action = real ? (item >> 28) & 7 : il::A_IDLE;
+                il::Lane L;
+                il::Globals g;
+                il::load_state<true>(tr.state + (int64_t)leaf * il::WORDS, li, L, g);
+                bool term, trunc;
+                const float r = il::step(L, li, g, action, term, trunc, 0xffffffffu);
+                if (real) {
+                    const int c = base + w;
+                    il::store_state(tr.state + (int64_t)c * il::WORDS, li, L, g);
+                    if (li == 0) write_child(a, c, leaf, action, (double)r, term, il::avail_mask(g.si));
                 }
             }
         } else if (M > 0) {
@@ -881,6 +909,8 @@ extern "C" int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* ro
         B2_REQUIRE(cfg->mdp.n_actions == cfg->n_actions, "mdp.n_actions != n_actions");
     } else if (cfg->env_kind == B2_ENV_HIGHWAY) {
         B2_REQUIRE(cfg->n_actions == B2_HW_ACTIONS, "HighwayLite has 5 actions");
+    } else if (cfg->env_kind == B2_ENV_INTERSECTION) {
+        B2_REQUIRE(cfg->n_actions == B2_IL_ACTIONS && cfg->n_models == 0, "IntersectionLite has 3 actions (no joint mode)");
     } else {
         set_error("unknown env_kind %d", cfg->env_kind);
         return B2_ERR_INVALID;
@@ -916,5 +946,39 @@ extern "C" int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* ro
     void* params[] = {&a};
     B2_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)wave::opd_wave_kernel, dim3(grid), dim3(wave::THREADS), params,
                                               smem, stream));
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batched IntersectionLite transition (b2_intersection_step): one scene per 16-lane group
+// ---------------------------------------------------------------------------
+namespace b2 {
+__global__ void __launch_bounds__(128) intersection_step_kernel(int32_t* states, const int32_t* actions, float* reward,
+                                                                int32_t* flags, int32_t* avail, int n_envs) {
+    const int gidx = (blockIdx.x * 128 + threadIdx.x) >> 4, li = threadIdx.x & 15;
+    const bool live = gidx < n_envs;
+    const int e = live ? gidx : n_envs - 1;
+    il::Lane L;
+    il::Globals g;
+    il::load_state<false>(states + (int64_t)e * il::WORDS, li, L, g);
+    bool term, trunc;
+    const float r = il::step(L, li, g, actions[e], term, trunc, 0xffffffffu);
+    if (live) {
+        il::store_state(states + (int64_t)e * il::WORDS, li, L, g);
+        if (li == 0) {
+            reward[e] = r;
+            flags[e] = (term ? 1 : 0) | (trunc ? 2 : 0);
+            if (avail) avail[e] = il::avail_mask(g.si);
+        }
+    }
+}
+}  // namespace b2
+
+extern "C" int b2_intersection_step(int32_t* states, const int32_t* actions, float* reward, int32_t* flags,
+                                    int32_t* avail_mask, int32_t n_envs, void* stream) {
+    B2_REQUIRE(states && actions && reward && flags && n_envs > 0, "null pointer / empty batch");
+    const int grid = (n_envs + 7) / 8;
+    b2::intersection_step_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(states, actions, reward, flags, avail_mask, n_envs);
+    B2_CUDA_CHECK(cudaGetLastError());
     return B2_OK;
 }

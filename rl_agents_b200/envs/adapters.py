@@ -16,6 +16,10 @@ def describe(env):
     d = EnvDescription()
     d.n_actions = int(env.action_space.n)
     kind = getattr(u, "b2_env_kind", None)
+    if kind == "intersection":
+        d.kind, d.mdp = _lib.ENV_INTERSECTION, None
+        d.root = np.ascontiguousarray(u.words, dtype=np.int32)
+        return d
     if kind == "highway" or (kind is None and hasattr(u, "words")):
         d.kind, d.mdp = _lib.ENV_HIGHWAY, None
         d.root = np.ascontiguousarray(u.words, dtype=np.int32)

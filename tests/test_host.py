@@ -267,3 +267,20 @@ def test_live_highway_env_object_is_packed_into_a_highway_lite_scene():
     env2.config["lanes_count"] = 3
     with pytest.raises(TypeError):
         describe(env2)
+
+
+def test_intersection_constants_match_the_spec():
+    from oracle import intersection as oit
+    src = open(os.path.join(ROOT, "rl_agents_b200", "csrc", "intersection_lite.cuh")).read()
+    consts = dict(re.findall(r"IL_CONST\((\w+),\s*(-?0x[0-9a-fA-F.]+p[+-]?\d+)f\)", src))
+    assert len(consts) >= 20
+    expect = {"DT": oit.DT, "KP_A": oit.KP_A, "APPROACH": oit.APPROACH, "ARC_LEFT": oit.ARC_LEFT, "ARC_RIGHT": oit.ARC_RIGHT,
+              "LEN_LEFT": oit.LEN[0], "LEN_STRAIGHT": oit.LEN[1], "LEN_RIGHT": oit.LEN[2],
+              "PRIO_END_LEFT": (oit.APPROACH + oit.BOX[0]) + oit.PRIO_PAST,
+              "PRIO_END_STRAIGHT": (oit.APPROACH + oit.BOX[1]) + oit.PRIO_PAST,
+              "PRIO_END_RIGHT": (oit.APPROACH + oit.BOX[2]) + oit.PRIO_PAST, "LENGTH": oit.LENGTH, "HIT_D2": oit.HIT_D2,
+              "ACC_MAX": oit.ACC_MAX, "OTHER_TS": oit.OTHER_TS, "STOP_LINE": oit.STOP_LINE, "YIELD_FROM": oit.YIELD_FROM,
+              "PRIO_FROM": oit.PRIO_FROM, "ENTRY_CLEAR": oit.ENTRY_CLEAR, "SPAWN_SPEED": oit.SPAWN_SPEED,
+              "SPEED_STEP": oit.SPEED_STEP}
+    for name, lit in consts.items():
+        assert np.float32(float.fromhex(lit)) == np.float32(expect[name]), name
