@@ -735,10 +735,30 @@ def other_paths(a, dev, world, rank):
         torch.cuda.empty_cache()
     except Exception as ex:
         out["mcts_c3_wavefront"] = {"error": repr(ex)[:300]}
-    # ---- C5-sized: ONE OPD decision, budget 1e6, sub-tree sharded (ShardedOPD, one all_reduce(MAX)) ----
+    # ---- C5: ONE OPD decision on IntersectionLite, budget 1e6 (333 333 expansions), gamma 0.9:
+    #      the whole tree on one GPU in waves, and sub-tree sharded over the ranks (one all_reduce(MAX)) ----
     try:
-        sh = D.ShardedOPD(1000000, 0.8, device=dev, wave_width=1024)
-        scene_np = make_scene(0)
+        from rl_agents_b200.engine.opd import OPDWaveEngine
+        from rl_agents_b200.envs.intersection_lite import make_scene as make_intersection
+        rows = []
+        sc = torch.tensor(make_intersection(0), dtype=torch.int32, device=dev)
+        for width in (1024, 4096):
+            eng = OPDWaveEngine(_lib.ENV_INTERSECTION, 3, 1000000, 0.9, width, device=dev)
+            ms = timed_ms(lambda: eng.plan(sc), reps=3)
+            res = eng.result.cpu().numpy()
+            rows.append({"width": width, "ms_per_decision": ms, "expansions_per_s": 333333 / (ms * 1e-3),
+                         "waves": int(res[0, 7]), "root_value_lower": float(eng.lower[0, 0].item())})
+            del eng
+        out["opd_c5_one_gpu_wavefront"] = {
+            "workload": "C5: ONE OPD decision on IntersectionLite (the repo's model of intersection-v0), budget 1e6 = "
+                        "333 333 expand() calls, gamma 0.9, the whole tree on ONE GPU in waves of `width` leaves "
+                        "(every rank runs the same decision; rank 0's time)", "rows": rows}
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["opd_c5_one_gpu_wavefront"] = {"error": repr(ex)[:300]}
+    try:
+        sh = D.ShardedOPD(1000000, 0.9, device=dev, wave_width=1024, env="intersection")
+        scene_np = make_intersection(0)
         sync()
         t0 = time.perf_counter()
         r = sh.decide(scene_np)
@@ -749,14 +769,15 @@ def other_paths(a, dev, world, rank):
         r = sh.decide(scene_np)
         torch.cuda.synchronize()
         dt = min(dt, max_over_ranks(time.perf_counter() - t0))
-        out["opd_1e6_subtree_sharded"] = {
-            "workload": "ONE OPD decision on HighwayLite (C5's env intersection-v0 is not modelled), budget 1e6, gamma 0.8, "
-                        "%d sub-trees dealt over %d GPU(s), each searched by its rank's whole GPU in waves of 1024 leaves" % (r["n_subtrees"], world),
-            "s_per_decision": dt, "expansions_per_s": 200000 / dt, "action": int(r["action"]),
+        out["opd_c5_subtree_sharded"] = {
+            "workload": "C5: ONE OPD decision on IntersectionLite, budget 1e6, gamma 0.9, tree-sharded: the root's depth-k "
+                        "sub-trees (%d) dealt over %d GPU(s), each searched by its rank's whole GPU in waves of 1024 leaves"
+                        % (r["n_subtrees"], world),
+            "s_per_decision": dt, "expansions_per_s": 333333 / dt, "action": int(r["action"]),
             "root_lower": float(r["root_lower"]),
             "collective": None if world == 1 else "one all_reduce(MAX) of the [n_subtrees, 2] bounds"}
     except Exception as ex:
-        out["opd_1e6_subtree_sharded"] = {"error": repr(ex)[:300]}
+        out["opd_c5_subtree_sharded"] = {"error": repr(ex)[:300]}
     return out
 
 

@@ -198,9 +198,12 @@ __device__ __forceinline__ float step(Lane& L, int li, Globals& g, int action, b
             const unsigned h = k * 2654435761u + 40503u;
             const int route = (int)((h >> 16) % (unsigned)N_ROUTES);
             const bool pres = (L.flags & 1) != 0;
+            // the spawn clock differs between the two scenes of a warp (leaves of different depths): this
+            // branch is uniform per 16-lane group only, so the votes synchronise the group, not the warp
             const unsigned half_shift = threadIdx.x & 16;
-            const unsigned blocked = (__ballot_sync(gmask, pres && L.route / 3 == route / 3 && L.s < ENTRY_CLEAR) >> half_shift) & 0xffffu;
-            const unsigned freem = (__ballot_sync(gmask, !pres && li > 0) >> half_shift) & 0xffffu;
+            const unsigned hmask = 0xffffu << half_shift;
+            const unsigned blocked = (__ballot_sync(hmask, pres && L.route / 3 == route / 3 && L.s < ENTRY_CLEAR) >> half_shift) & 0xffffu;
+            const unsigned freem = (__ballot_sync(hmask, !pres && li > 0) >> half_shift) & 0xffffu;
             if (blocked == 0 && freem != 0 && li == __ffs(freem) - 1) {
                 L.s = 0.0f; L.v = SPAWN_SPEED; L.route = route; L.flags = 1;
             }

@@ -316,13 +316,19 @@ class ShardedOPD(object):
     evenly instead of greedily); with world == 1 the same decomposition runs on one GPU, which is
     what the parity test compares against."""
 
-    def __init__(self, budget, gamma, terminal_reward=0.0, group=None, device="cuda", max_depth=3, wave_width=0):
+    def __init__(self, budget, gamma, terminal_reward=0.0, group=None, device="cuda", max_depth=3, wave_width=0,
+                 env="highway"):
         """wave_width = 0: every sub-tree is searched in the reference's strict best-first order (one CTA per
         sub-tree, all of a rank's sub-trees in one launch).  wave_width = K > 0: every sub-tree is searched by
         the rank's whole GPU in waves of K leaves (b2_opd_plan_wave), one sub-tree after the other."""
         self.budget, self.gamma, self.terminal_reward = int(budget), float(gamma), float(terminal_reward)
         self.group, self.device, self.max_depth = group, device, max_depth
         self.wave_width = int(wave_width)
+        if env not in ("highway", "intersection"):
+            raise ValueError("env must be 'highway' or 'intersection'")
+        self.env = env
+        if env == "intersection" and self.wave_width <= 0:
+            self.wave_width = 1            # IntersectionLite lives in the wavefront kernel (width 1 = strict order)
 
     def _world(self):
         import torch.distributed as dist
@@ -340,15 +346,20 @@ class ShardedOPD(object):
         act = torch.tensor(actions_list, dtype=torch.int32, device=self.device)
         rew = torch.empty(n, dtype=torch.float32, device=self.device)
         flg = torch.empty(n, dtype=torch.int32, device=self.device)
-        _lib.check(lib.b2_highway_step(_lib.ptr(st), _lib.ptr(act), _lib.ptr(rew), _lib.ptr(flg), None, n,
-                                       _lib.current_stream()))
+        step = lib.b2_highway_step if self.env == "highway" else lib.b2_intersection_step
+        _lib.check(step(_lib.ptr(st), _lib.ptr(act), _lib.ptr(rew), _lib.ptr(flg), None, n, _lib.current_stream()))
         return st.cpu().numpy(), rew.cpu().numpy().astype(np.float64), (flg.cpu().numpy() & 1).astype(bool)
 
     def decide(self, root_words):
         import torch
         from rl_agents_b200 import _lib
         from rl_agents_b200.engine.opd import OPDEngine
-        from rl_agents_b200.envs.highway_lite import available_actions
+        if self.env == "highway":
+            from rl_agents_b200.envs.highway_lite import available_actions
+            kind, n_act = _lib.ENV_HIGHWAY, 5
+        else:
+            from rl_agents_b200.envs.intersection_lite import available_actions
+            kind, n_act = _lib.ENV_INTERSECTION, 3
         world, rank = self._world()
         g = self.gamma
         # top of the tree, replicated: nodes = dicts in creation order
@@ -374,10 +385,10 @@ class ShardedOPD(object):
         subtrees = [i for i in frontier if not top[i]["done"] and not top[i]["children"]]
         table = torch.full((max(len(subtrees), 1), 2), -np.inf, dtype=torch.float64, device=self.device)
         mine = [j for j in range(len(subtrees)) if j % world == rank]
-        per_tree = max((self.budget - spent) // max(len(subtrees), 1), 5)
+        per_tree = max((self.budget - spent) // max(len(subtrees), 1), n_act)
         if mine and self.wave_width > 0:
             from rl_agents_b200.engine.opd import OPDWaveEngine
-            eng = OPDWaveEngine(_lib.ENV_HIGHWAY, 5, per_tree, g, self.wave_width, self.terminal_reward, device=self.device)
+            eng = OPDWaveEngine(kind, n_act, per_tree, g, self.wave_width, self.terminal_reward, device=self.device)
             for j in mine:
                 node = top[subtrees[j]]
                 eng.plan(torch.tensor(node["words"], dtype=torch.int32, device=self.device))

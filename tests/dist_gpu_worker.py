@@ -81,6 +81,9 @@ def main():
     out["sharded_action"] = int(sharded["action"])
     out["sharded_children"] = {str(k): list(v) for k, v in sharded["children"].items()}
     out["sharded_root"] = [sharded["root_lower"], sharded["root_upper"], sharded["n_subtrees"]]
+    from rl_agents_b200.envs.intersection_lite import make_scene as make_intersection
+    sh_il = ShardedOPD(3000, 0.9, device=dev, env="intersection", wave_width=16).decide(make_intersection(1))
+    out["sharded_il"] = [int(sh_il["action"]), sh_il["root_lower"], sh_il["root_upper"], sh_il["n_subtrees"]]
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:

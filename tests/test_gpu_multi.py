@@ -41,6 +41,12 @@ def test_two_rank_vi_and_root_parallel_mcts():
     assert {str(k): list(v) for k, v in single["children"].items()} == res[0]["sharded_children"]
     assert int(single["action"]) == res[0]["sharded_action"]
     assert [single["root_lower"], single["root_upper"], single["n_subtrees"]] == res[0]["sharded_root"]
+    # the same on IntersectionLite (C5's env model), sub-trees searched in waves
+    from rl_agents_b200.envs.intersection_lite import make_scene as make_intersection
+    single_il = ShardedOPD(3000, 0.9, device="cuda:0", env="intersection", wave_width=16).decide(make_intersection(1))
+    assert res[0]["sharded_il"] == res[1]["sharded_il"]
+    assert res[0]["sharded_il"] == [int(single_il["action"]), single_il["root_lower"], single_il["root_upper"],
+                                    single_il["n_subtrees"]]
 
 
 def test_sharded_opd_single_rank_is_consistent_with_plain_opd():
