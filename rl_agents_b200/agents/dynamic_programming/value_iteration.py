@@ -65,7 +65,23 @@ class ValueIterationAgent(AbstractAgent):
         return q.cpu().numpy()
 
     def get_state_value(self):
-        return self.best_action_value(self.state_action_value)
+        """value_iteration.py:37-40: the reference runs a SEPARATE fixed-point iteration on V (allclose tested on V,
+        which can stop at an earlier iterate than the iteration on Q): V' = max_a B(V) with the device sweep, the
+        allclose test of fixed_point_iteration (:65-73) on the host, returning the previous iterate."""
+        from rl_agents_b200.engine.vi import VIEngine
+        mdp = self.mdp
+        eng = VIEngine(mdp.mode, mdp.transition, mdp.reward, mdp.terminal, nxt=getattr(mdp, "next", None),
+                       gamma=self.config["gamma"], rtol=0.0, atol=-1.0)      # the kernel's own Q test never fires
+        iterations = int(self.config["iterations"])
+        eng.reset(iterations)
+        v = np.zeros(eng.n_states)
+        for k in range(iterations):
+            eng.sweep(k)
+            v_next = eng.v[(k + 1) & 1].cpu().numpy()
+            if np.allclose(v, v_next):
+                break
+            v = v_next
+        return v
 
     @staticmethod
     def best_action_value(action_values):

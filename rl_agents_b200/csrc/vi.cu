@@ -493,6 +493,7 @@ using namespace b2;
 extern "C" int b2_vi_sweep(const b2_vi_problem* p, const double* v_in, const double* q_old, double* q_new,
                            double* v_out, int32_t* viol, int32_t sweep_index, void* stream_) {
     B2_REQUIRE(p && v_in && q_old && q_new && v_out && viol, "null pointer");
+    B2_REQUIRE(p->reward && p->transition && p->terminal, "MDP tables (reward / transition / terminal) missing");
     B2_REQUIRE(p->n_actions > 0 && p->row_end >= p->row_begin && p->row_end <= p->n_states, "bad shape");
     B2_REQUIRE(sweep_index >= 0, "sweep_index < 0");
     cudaStream_t stream = (cudaStream_t)stream_;

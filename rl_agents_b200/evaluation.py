@@ -32,7 +32,10 @@ def run_batched_episodes(planner, seeds, budget, gamma, max_steps=40, device="cu
         eng = OPDEngine(_lib.ENV_HIGHWAY, n, 5, budget, gamma, kw.get("terminal_reward", 0.0), device=dev)
     elif planner == "mcts":
         episodes, horizon = allocation(budget, gamma)
-        eng = MCTSEngine(_lib.ENV_HIGHWAY, n, 5, episodes, horizon, gamma, kw.get("temperature", 2 / (1 - 0.8)), device=dev)
+        from rl_agents_b200.agents.tree_search.mcts import MCTS
+        # the reference's default temperature comes from the CLASS default gamma (mcts.py:120-127), not the configured one
+        eng = MCTSEngine(_lib.ENV_HIGHWAY, n, 5, episodes, horizon, gamma,
+                         kw.get("temperature", MCTS.default_config()["temperature"]), device=dev)
     elif planner == "olop":
         episodes, horizon = allocation(max(5, budget), gamma)
         ub = kw.get("upper_bound", {"type": "kullback-leibler", "time": "global", "threshold": "2*np.log(time)"})

@@ -82,6 +82,15 @@ def test_vi_agent_matches_reference():
     assert np.array_equal(agent.state_action_value, np.array(g["q"]))
     assert agent.act(0) == g["act0"] == 3
     assert agent.plan(0) == [3]
+    # get_state_value: the reference's separate fixed point on V (value_iteration.py:37-40), restated with numpy
+    v = np.zeros(100)
+    for _ in range(100):
+        nv = planners.bellman_expectation("deterministic", M["large1_T"], M["large1_R"], M["large1_term"].astype(bool), v,
+                                          0.9).max(axis=-1)
+        if np.allclose(v, nv):
+            break
+        v = nv
+    assert np.array_equal(agent.get_state_value(), v)
     # non-finite env path: to_finite_mdp() re-solved on every act (value_iteration.py:31-34)
     agent2 = ValueIterationAgent(oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"]),
                                  {"gamma": 1.0, "iterations": 2})
