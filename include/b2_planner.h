@@ -247,6 +247,48 @@ int64_t b2_opd_wave_workspace_bytes(const b2_opd_wave_config* cfg);
 int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* root_state, const b2_opd_tree* tree,
                      void* workspace, int8_t* plan, int32_t* result, void* stream);
 
+/* ------------------------------------------------------------------------
+ * GBOP-T -- rl_agents/agents/tree_search/state_aware.py (StateAwarePlanner), deterministic finite MDPs:
+ * OPD whose leaf bounds share one value table per STATE (:66-68), tightened by a breadth-first backup through
+ * the nodes aggregated by state (:42-64), with pruning of dominated leaves after every expansion (:28-40).
+ * A batch of n_trees independent decisions, one warp per tree, node order / leaves / state values exactly
+ * the reference's.
+ * ---------------------------------------------------------------------- */
+typedef struct b2_gbop_config {
+    int32_t n_trees;
+    int32_t n_actions;
+    int32_t n_expansions;        /* budget // n_actions (deterministic.py:118)      */
+    int32_t node_capacity;       /* per tree, >= 1 + n_expansions * n_actions       */
+    int32_t plan_capacity;
+    int32_t queue_capacity;      /* entries of the backup FIFO (result[7] = 1 on overflow) */
+    int32_t backup_aggregated_nodes;   /* config key of the same name (:80-85)      */
+    int32_t prune_suboptimal_leaves;
+    double gamma;
+    double default_value;        /* 1 / (1 - gamma), host float (:76-77)            */
+    double accuracy_scale;       /* accuracy * (1 - gamma), host float (:61)        */
+    const double* gamma_pow;     /* [n_expansions+2] gamma**d                       */
+    const double* terminal_bonus;/* [n_expansions+2] terminal_reward * gamma**d / (1 - gamma) */
+    b2_finite_mdp mdp;
+} b2_gbop_config;
+
+typedef struct b2_gbop_tree {    /* [n_trees, node_capacity] each */
+    int32_t* parent;
+    int32_t* first_child;
+    int32_t* depth;
+    int32_t* count;
+    int32_t* meta;               /* action | n_children << 8 | done << 16 | still-a-leaf << 17 */
+    double* reward;
+    double* lower;               /* value_lower (the path sum: GBOP-T never backs it up) */
+    int32_t* obs;                /* the state the node reached                      */
+} b2_gbop_tree;
+
+int64_t b2_gbop_workspace_bytes(const b2_gbop_config* cfg);
+/* The first 8 * n_states bytes of every tree's workspace slice hold the state value table afterwards.
+ * result: int32 [n_trees, B2_OPD_RESULT_WORDS]: [0] n_nodes [1] n_leaves [4] error [5] plan_len [6] tie_node
+ * [7] queue overflow [8] expansions done. */
+int b2_gbop_plan(const b2_gbop_config* cfg, const int32_t* root_states, const b2_gbop_tree* tree, void* workspace,
+                 int8_t* plan, int32_t* result, void* stream);
+
 /* Host-buffer convenience API (callers that do not manage CUDA memory: plain C, cgo, JNI ...).
  * A handle owns the device arena of a batch of trees; *_host pointers are ordinary host memory
  * (pinned memory makes the copies asynchronous); b2_opd_plan_host is synchronous. */

@@ -59,6 +59,17 @@ class OPDWaveConfig(ctypes.Structure):
                 ("model_mdps", FiniteMDP * 8)]
 
 
+class GBOPConfig(ctypes.Structure):
+    _fields_ = [("n_trees", c_int32), ("n_actions", c_int32), ("n_expansions", c_int32), ("node_capacity", c_int32),
+                ("plan_capacity", c_int32), ("queue_capacity", c_int32), ("backup_aggregated_nodes", c_int32),
+                ("prune_suboptimal_leaves", c_int32), ("gamma", c_double), ("default_value", c_double),
+                ("accuracy_scale", c_double), ("gamma_pow", c_void_p), ("terminal_bonus", c_void_p), ("mdp", FiniteMDP)]
+
+
+class GBOPTree(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("parent", "first_child", "depth", "count", "meta", "reward", "lower", "obs")]
+
+
 class OPDTree(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("parent", "first_child", "depth", "count", "meta", "reward",
                                         "lower", "upper", "state")]
@@ -128,6 +139,9 @@ EXPORTS = {
     "b2_opd_wave_workspace_bytes": (c_int64, [ctypes.POINTER(OPDWaveConfig)]),
     "b2_opd_plan_wave": (c_int, [ctypes.POINTER(OPDWaveConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
+    "b2_gbop_workspace_bytes": (c_int64, [ctypes.POINTER(GBOPConfig)]),
+    "b2_gbop_plan": (c_int, [ctypes.POINTER(GBOPConfig), c_void_p, ctypes.POINTER(GBOPTree), c_void_p, c_void_p,
+                             c_void_p, c_void_p]),
     "b2_opd_create": (c_int, [ctypes.POINTER(OPDHostConfig), ctypes.POINTER(c_void_p)]),
     "b2_opd_destroy": (None, [c_void_p]),
     "b2_opd_plan_capacity": (c_int32, [c_void_p]),
