@@ -104,7 +104,7 @@ struct SelShared {
 // One segment's arrivals, in episode order: pick the best child by (score, counter-based tie-break), bump its
 // virtual count, record the path; then split the segment into the children's segments (stable partition).
 // `key_of(c, k)` is the order-preserving image of child c's score after k virtual visits.
-template <typename KeyOf>
+template <bool RUNS, typename KeyOf>
 __device__ __forceinline__ void route_segment(const Args& a, SelShared& sh, int cur, int nxt, int w0, int d, int start,
                                               int m, int fc, int n, KeyOf key_of) {
     const int H = a.cfg.horizon;
@@ -115,31 +115,57 @@ __device__ __forceinline__ void route_segment(const Args& a, SelShared& sh, int 
         vc[c] = 0;
         key[c] = c < n ? key_of(c, 0) : (long long)0x8000000000000000ull;      // below every real score
     }
-    for (int i = 0; i < m; ++i) {
-        const int j = sh.order[cur][start + i];
+    for (int i = 0; i < m;) {
         long long best = key[0];
 #pragma unroll
         for (int c = 1; c < MAX_A; ++c) best = key[c] > best ? key[c] : best;
         int ties = 0;
-#pragma unroll
-        for (int c = 0; c < MAX_A; ++c) ties += key[c] == best ? 1 : 0;
-        int pick = ties > 1 ? wave_random(a.cfg.seed, w0 + j, d, 0, ties) : 0, sel = 0;
+        long long second = (long long)0x8000000000000000ull;                    // best key among the others
 #pragma unroll
         for (int c = 0; c < MAX_A; ++c) {
-            if (key[c] == best) {
-                if (pick == 0) sel = c;
-                --pick;
+            ties += key[c] == best ? 1 : 0;
+            second = (key[c] != best && key[c] > second) ? key[c] : second;
+        }
+        int sel = 0, run = 1;
+        if (ties > 1) {
+            int pick = wave_random(a.cfg.seed, w0 + sh.order[cur][start + i], d, 0, ties);
+#pragma unroll
+            for (int c = 0; c < MAX_A; ++c) {
+                if (key[c] == best) {
+                    if (pick == 0) sel = c;
+                    --pick;
+                }
             }
+        } else {
+#pragma unroll
+            for (int c = 0; c < MAX_A; ++c) sel = key[c] == best ? c : sel;
+            if (RUNS) {
+                // a child's score only falls as its virtual count grows: the unique best child keeps winning
+                // until its score reaches the runner-up's -- binary search for that point in its score row
+                int base = 0;
+#pragma unroll
+                for (int c = 0; c < MAX_A; ++c) base = c == sel ? vc[c] : base;
+                int lo = 1, hi = m - i;                     // the run is in [lo, hi]
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;     // can the run be `mid` long?  (pick mid-1 still wins)
+                    if (key_of(sel, base + mid - 1) > second) lo = mid; else hi = mid - 1;
+                }
+                run = lo;
+            }
+        }
+        for (int q = 0; q < run; ++q) {
+            const int j = sh.order[cur][start + i + q];
+            sh.pick[start + i + q] = (unsigned char)sel;
+            a.paths[(int64_t)j * H + d] = fc + sel;
         }
 #pragma unroll
         for (int c = 0; c < MAX_A; ++c) {
             if (c == sel) {
-                vc[c] += 1;
+                vc[c] += run;
                 key[c] = key_of(c, vc[c]);
             }
         }
-        sh.pick[start + i] = (unsigned char)sel;
-        a.paths[(int64_t)j * H + d] = fc + sel;
+        i += run;
     }
     int cstart[MAX_A];
     int run = start;
@@ -221,7 +247,7 @@ __device__ void select_wave(const Args& a, SelShared& sh, long long* table, int 
                 continue;
             }
             const double tnp = T * (double)n * (1.0 / (double)n);
-            route_segment(a, sh, cur, nxt, w0, d, start, m, fc, n, [&](int c, int k) {
+            route_segment<false>(a, sh, cur, nxt, w0, d, start, m, fc, n, [&](int c, int k) {
                 double v = 0.0;
                 int base = 0;
 #pragma unroll
@@ -246,7 +272,7 @@ __device__ void select_wave(const Args& a, SelShared& sh, long long* table, int 
         if (tid < n_big) {
             const int s = sh.big_seg[tid], start = sh.seg_start[cur][s], m = sh.seg_len[cur][s];
             const long long* tab = table + sh.big_off[tid];
-            route_segment(a, sh, cur, nxt, w0, d, start, m, sh.big_fc[tid], sh.big_n[tid],
+            route_segment<true>(a, sh, cur, nxt, w0, d, start, m, sh.big_fc[tid], sh.big_n[tid],
                           [&](int c, int k) { return tab[c * (m + 1) + k]; });
         }
         __syncthreads();
