@@ -37,6 +37,13 @@ def allgather_slabs(full, n, group=None):
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if full.is_cuda and dist.get_backend(group) == "gloo":
+        # gloo has no all_gather for device tensors: stage through the host (CPU-backend tests of the device
+        # path, e.g. two ranks sharing one GPU; the production backend is NCCL or the fused peer-memory sweep)
+        host = full[:n].cpu()
+        allgather_slabs(host, n, group)
+        full[:n].copy_(host)
+        return full
     sizes = slab_sizes(n, world)
     if len(set(sizes)) == 1:
         b, e = shard_range(n, rank, world)
