@@ -289,6 +289,31 @@ int64_t b2_gbop_workspace_bytes(const b2_gbop_config* cfg);
 int b2_gbop_plan(const b2_gbop_config* cfg, const int32_t* root_states, const b2_gbop_tree* tree, void* workspace,
                  int8_t* plan, int32_t* result, void* stream);
 
+/* GBOP-D -- rl_agents/agents/tree_search/graph_based.py (GraphBasedPlanner), deterministic finite MDPs: one graph
+ * node per state with value_lower / value_upper, optimistic descent to an unexpanded state, breadth-first partial
+ * value iteration through the expanded parents (pushed in ascending state id; the reference iterates a Python set).
+ * n_trees independent decisions, one warp each; rng: numpy PCG64 states [n_trees, 6] consumed by the tie-breaks of
+ * sampling_rule (:22-30) exactly as Generator.choice does, advanced in place. */
+typedef struct b2_gbopd_config {
+    int32_t n_trees;
+    int32_t n_actions;
+    int32_t n_epochs;            /* budget // n_actions (:119)                       */
+    int32_t sampling_timeout;    /* config["sampling_timeout"] (default 100)         */
+    int32_t plan_capacity;       /* >= sampling_timeout                              */
+    int32_t queue_capacity;      /* per tree; result[7] = 1 on overflow              */
+    double gamma;
+    double default_value;        /* 1 / (1 - gamma) (:17)                            */
+    double accuracy;             /* config["accuracy"] (default 1e-2, :74)           */
+    b2_finite_mdp mdp;           /* terminal unused: GBOP-D ignores `done` (:46)     */
+    const int32_t* rev_ptr;      /* [S+1] reverse transitions: states p with T[p, a] == s for some a, */
+    const int32_t* rev_idx;      /* ascending, unique                                */
+} b2_gbopd_config;
+/* lower / upper: double [n_trees, S]; flags: uint8 [n_trees, S] (bit0 node exists, bit1 expanded); queue: int32
+ * [n_trees, queue_capacity] scratch; plan: int8 [n_trees, plan_capacity]; result: [0] nodes [1] expansions
+ * [2] epochs that found no sink [5] plan_len [7] queue overflow. */
+int b2_gbopd_plan(const b2_gbopd_config* cfg, const int32_t* root_states, double* lower, double* upper, uint8_t* flags,
+                  int32_t* queue, uint64_t* rng, int8_t* plan, int32_t* result, void* stream);
+
 /* Host-buffer convenience API (callers that do not manage CUDA memory: plain C, cgo, JNI ...).
  * A handle owns the device arena of a batch of trees; *_host pointers are ordinary host memory
  * (pinned memory makes the copies asynchronous); b2_opd_plan_host is synchronous. */

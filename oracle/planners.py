@@ -232,6 +232,70 @@ def robust_plan(envs, budget, gamma, terminal_reward=0.0, np_random=None, width=
     return greedy_plan(t, t.lower, np_random), t
 
 
+def graph_based_plan(env, observation, budget, gamma, np_random, accuracy=1e-2, sampling_timeout=100):
+    """GraphBasedPlanner.plan (GBOP-D, rl_agents/agents/tree_search/graph_based.py:84-138) on an env whose
+    observations are hashable state ids.  One graph node per state with value_lower / value_upper (:12-20); an epoch
+    walks from the root along the optimistic action (:22-30, random tie-break through the planner RNG) to a node
+    without children, expands it (:38-52; `done` is ignored there) and runs partial_value_iteration (:63-75): a FIFO
+    of nodes whose two bounds are re-backed-up, pushing a node's parents while the change exceeds `accuracy`.
+    The reference pushes `list(node.parents)` -- a Python set of objects, i.e. an order that depends on memory
+    addresses; this restatement (and the device planner) pushes the parents in ASCENDING state id.  With
+    accuracy = 0 the iteration runs to its fixed point, which does not depend on that order.
+    Returns (plan, nodes) with nodes[s] = dict(lower, upper, expanded)."""
+    A = env.action_space.n
+    nodes = {}
+
+    def get_node(o, state=None):
+        if o not in nodes:
+            nodes[o] = dict(state=state, lower=0.0, upper=1 / (1 - gamma), rewards={}, children={}, parents=set())
+        if state is not None and nodes[o]["state"] is None:
+            nodes[o]["state"] = state
+        return nodes[o]
+
+    def backup(n, field):
+        return {a: n["rewards"][a] + gamma * nodes[n["children"][a]][field] for a in n["children"]}
+
+    root = get_node(observation, env)
+    for _ in range(int(budget) // A):
+        o = observation
+        for _k in range(sampling_timeout):
+            n = nodes[o]
+            if not n["children"]:
+                for a in _available_actions(n["state"]):                      # expand (:38-52)
+                    st = copy.deepcopy(n["state"])
+                    nxt, reward, _done = st.step(a)[:3]
+                    child = get_node(nxt)
+                    child["state"] = st
+                    child["parents"].add(o)
+                    n["rewards"][a] = reward
+                    n["children"][a] = nxt
+                queue = [o]                                                   # partial_value_iteration (:63-75)
+                while queue:
+                    m = nodes[queue.pop(0)]
+                    delta = 0
+                    for field in ("lower", "upper"):
+                        bound = np.amax(list(backup(m, field).values()))
+                        delta = max(delta, abs(m[field] - bound))
+                        m[field] = bound
+                    if delta > accuracy:
+                        queue.extend(sorted(m["parents"]))
+                break
+            q = backup(n, "upper")                                            # sampling_rule (:22-30)
+            actions = list(q.keys())
+            x = np.array([q[a] for a in actions])
+            indices = np.nonzero(x == np.amax(x))[0]
+            o = n["children"][actions[np_random.choice(indices)]]
+    plan, n = [], root
+    for _ in range(sampling_timeout):                                         # get_plan (:126-135)
+        if not n["children"]:
+            break
+        ql = backup(n, "lower")
+        a = max(ql.items(), key=lambda kv: kv[1])[0]
+        plan.append(a)
+        n = nodes[n["children"][a]]
+    return plan, {o: dict(lower=float(n["lower"]), upper=float(n["upper"]), expanded=bool(n["children"])) for o, n in nodes.items()}
+
+
 def greedy_plan(t, values, np_random):
     """AbstractPlanner.get_plan (abstract.py:143-156) with
     DeterministicNode.selection_rule (deterministic.py:21-26): arg-max of the

@@ -66,6 +66,12 @@ class GBOPConfig(ctypes.Structure):
                 ("accuracy_scale", c_double), ("gamma_pow", c_void_p), ("terminal_bonus", c_void_p), ("mdp", FiniteMDP)]
 
 
+class GBOPDConfig(ctypes.Structure):
+    _fields_ = [("n_trees", c_int32), ("n_actions", c_int32), ("n_epochs", c_int32), ("sampling_timeout", c_int32),
+                ("plan_capacity", c_int32), ("queue_capacity", c_int32), ("gamma", c_double), ("default_value", c_double),
+                ("accuracy", c_double), ("mdp", FiniteMDP), ("rev_ptr", c_void_p), ("rev_idx", c_void_p)]
+
+
 class GBOPTree(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("parent", "first_child", "depth", "count", "meta", "reward", "lower", "obs")]
 
@@ -142,6 +148,7 @@ EXPORTS = {
     "b2_gbop_workspace_bytes": (c_int64, [ctypes.POINTER(GBOPConfig)]),
     "b2_gbop_plan": (c_int, [ctypes.POINTER(GBOPConfig), c_void_p, ctypes.POINTER(GBOPTree), c_void_p, c_void_p,
                              c_void_p, c_void_p]),
+    "b2_gbopd_plan": (c_int, [ctypes.POINTER(GBOPDConfig)] + [c_void_p] * 9),
     "b2_opd_create": (c_int, [ctypes.POINTER(OPDHostConfig), ctypes.POINTER(c_void_p)]),
     "b2_opd_destroy": (None, [c_void_p]),
     "b2_opd_plan_capacity": (c_int32, [c_void_p]),

@@ -12,6 +12,7 @@
 //     node of the same state has a bound at least as good at no smaller depth.  Leaves of different states do
 //     not interact, so the prune runs one lane per state, each walking its state's list backwards.
 #include "common.cuh"
+#include "pcg64.cuh"
 
 namespace b2 {
 
@@ -206,6 +207,127 @@ __global__ void __launch_bounds__(128) gbop_finite_kernel(GbopArgs a) {
     res[7] = overflow; res[8] = n_exp;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// GBOP-D (graph-based optimistic planning) -- GraphBasedPlanner.plan (graph_based.py:84-138), deterministic
+// finite MDPs: one graph node per STATE with a lower and an upper value bound.  An epoch walks from the root along
+// the optimistic action (random tie-break on the planner's numpy PCG64 stream) to a state without children,
+// expands it and re-backs-up both bounds breadth first through the expanded parents (reverse transition CSR
+// built on the host; the reference's `list(node.parents)` is a Python set, here: ascending state id).
+// One warp per decision, the epoch loop on its first lane.
+// ---------------------------------------------------------------------------------------------------------
+struct GbopdArgs {
+    b2_gbopd_config cfg;
+    const int32_t* root_states;
+    double* lower;          // [n_trees, S]
+    double* upper;          // [n_trees, S]
+    uint8_t* flags;         // [n_trees, S] bit0 node exists, bit1 expanded
+    int32_t* queue;         // [n_trees, queue_capacity]
+    uint64_t* rng;          // [n_trees, 6]
+    int8_t* plan;
+    int32_t* result;
+};
+
+__global__ void __launch_bounds__(128) gbopd_finite_kernel(GbopdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int tree = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (tree >= a.cfg.n_trees) return;
+    const b2_finite_mdp& m = a.cfg.mdp;
+    const int S = m.n_states, A = a.cfg.n_actions;
+    double* lo = a.lower + (int64_t)tree * S;
+    double* up = a.upper + (int64_t)tree * S;
+    uint8_t* fl = a.flags + (int64_t)tree * S;
+    int32_t* queue = a.queue + (int64_t)tree * a.cfg.queue_capacity;
+    for (int s = lane; s < S; s += 32) { lo[s] = 0.0; up[s] = a.cfg.default_value; fl[s] = 0; }
+    __syncwarp();
+    if (lane != 0) return;
+    Pcg64 rng;
+    rng.load(a.rng + (int64_t)tree * B2_PCG64_STATE_WORDS);
+    const int root = a.root_states[tree];
+    const double gamma = a.cfg.gamma;
+    fl[root] = 1;                                                    // get_node(observation) (:110-116)
+    int overflow = 0, expansions = 0, loops = 0;
+    for (int epoch = 0; epoch < a.cfg.n_epochs && !overflow; ++epoch) {
+        int s = root;
+        bool sink = false;
+        for (int k = 0; k < a.cfg.sampling_timeout; ++k) {
+            if (!(fl[s] & 2)) {
+                // expand (:38-52): children = T[s, :], rewards = R[s, :], this state joins its children's parents
+                fl[s] |= 2;
+                for (int act = 0; act < A; ++act) fl[m.transition[(int64_t)s * A + act]] |= 1;
+                ++expansions;
+                // partial_value_iteration (:63-75)
+                int qh = 0, qt = 0;
+                queue[qt++] = s;
+                while (qh < qt) {
+                    const int node = queue[qh++];
+                    double bl = -INFINITY, bu = -INFINITY;
+                    for (int act = 0; act < A; ++act) {
+                        const int c = m.transition[(int64_t)node * A + act];
+                        const double r = m.reward[(int64_t)node * A + act];
+                        const double vl = r + gamma * lo[c], vu = r + gamma * up[c];
+                        bl = vl > bl ? vl : bl;
+                        bu = vu > bu ? vu : bu;
+                    }
+                    double delta = fabs(lo[node] - bl);
+                    lo[node] = bl;
+                    const double du = fabs(up[node] - bu);
+                    delta = du > delta ? du : delta;
+                    up[node] = bu;
+                    if (delta > a.cfg.accuracy) {
+                        for (int e = a.cfg.rev_ptr[node]; e < a.cfg.rev_ptr[node + 1]; ++e) {
+                            const int p = a.cfg.rev_idx[e];
+                            if (fl[p] & 2) {
+                                if (qt < a.cfg.queue_capacity) queue[qt++] = p;
+                                else overflow = 1;
+                            }
+                        }
+                    }
+                }
+                sink = true;
+                break;
+            }
+            // sampling_rule (:22-30): optimistic action, random_argmax over the tied maxima
+            double q[GBOP_MAX_BRANCH], best = -INFINITY;
+            int ties = 0;
+            for (int act = 0; act < A; ++act) {
+                q[act] = m.reward[(int64_t)s * A + act] + gamma * up[m.transition[(int64_t)s * A + act]];
+                if (q[act] > best) { best = q[act]; ties = 1; }
+                else if (q[act] == best) ++ties;
+            }
+            int pick = (int)rng.integers((uint32_t)ties), sel = 0;
+            for (int act = 0; act < A; ++act) {
+                if (q[act] == best) {
+                    if (pick == 0) sel = act;
+                    --pick;
+                }
+            }
+            s = m.transition[(int64_t)s * A + sel];
+        }
+        if (!sink) ++loops;        // "could not find a sink" (:104-106)
+    }
+    rng.store(a.rng + (int64_t)tree * B2_PCG64_STATE_WORDS);
+    // get_plan (:126-135): conservative action (first max of the lower-bound backups)
+    int8_t* plan = a.plan + (int64_t)tree * a.cfg.plan_capacity;
+    int node = root, len = 0;
+    for (int k = 0; k < a.cfg.sampling_timeout; ++k) {
+        if (!(fl[node] & 2)) break;
+        double best = -INFINITY;
+        int sel = 0;
+        for (int act = 0; act < A; ++act) {
+            const double v = m.reward[(int64_t)node * A + act] + gamma * lo[m.transition[(int64_t)node * A + act]];
+            if (v > best) { best = v; sel = act; }
+        }
+        if (len < a.cfg.plan_capacity) plan[len] = (int8_t)sel;
+        ++len;
+        node = m.transition[(int64_t)node * A + sel];
+    }
+    int n_nodes = 0;
+    for (int s2 = 0; s2 < S; ++s2) n_nodes += fl[s2] & 1;
+    int32_t* res = a.result + (int64_t)tree * B2_OPD_RESULT_WORDS;
+    res[0] = n_nodes; res[1] = expansions; res[2] = loops; res[3] = 0; res[4] = 0; res[5] = len; res[6] = -1;
+    res[7] = overflow;
+}
+
 static int64_t gbop_ws_per_tree(const b2_gbop_config* c) {
     int64_t b = (int64_t)c->mdp.n_states * 16 + (int64_t)c->node_capacity * 8 + ((int64_t)c->n_expansions + 1) * 4 +
                 (int64_t)c->queue_capacity * 4;
@@ -235,6 +357,23 @@ extern "C" int b2_gbop_plan(const b2_gbop_config* cfg, const int32_t* root_state
     a.cfg = *cfg; a.tree = *tree; a.root_states = root_states; a.workspace = (char*)workspace;
     a.ws_per_tree = gbop_ws_per_tree(cfg); a.plan = plan; a.result = result;
     gbop_finite_kernel<<<(cfg->n_trees + 3) / 4, 128, 0, (cudaStream_t)stream>>>(a);
+    B2_CUDA_CHECK(cudaGetLastError());
+    return B2_OK;
+}
+
+extern "C" int b2_gbopd_plan(const b2_gbopd_config* cfg, const int32_t* root_states, double* lower, double* upper,
+                             uint8_t* flags, int32_t* queue, uint64_t* rng, int8_t* plan, int32_t* result, void* stream) {
+    B2_REQUIRE(cfg && root_states && lower && upper && flags && queue && rng && plan && result, "null pointer");
+    B2_REQUIRE(cfg->n_trees > 0 && cfg->n_epochs >= 0 && cfg->sampling_timeout > 0, "bad batch / budget");
+    B2_REQUIRE(cfg->n_actions > 0 && cfg->n_actions <= GBOP_MAX_BRANCH, "n_actions must be in 1..8");
+    B2_REQUIRE(cfg->mdp.transition && cfg->mdp.reward && cfg->mdp.n_states > 0 && cfg->mdp.n_actions == cfg->n_actions,
+               "finite MDP tables missing");
+    B2_REQUIRE(cfg->rev_ptr && cfg->rev_idx, "reverse transition CSR missing");
+    B2_REQUIRE(cfg->queue_capacity > 0 && cfg->plan_capacity > 0, "capacities must be positive");
+    GbopdArgs a;
+    a.cfg = *cfg; a.root_states = root_states; a.lower = lower; a.upper = upper; a.flags = flags; a.queue = queue;
+    a.rng = rng; a.plan = plan; a.result = result;
+    gbopd_finite_kernel<<<(cfg->n_trees + 3) / 4, 128, 0, (cudaStream_t)stream>>>(a);
     B2_CUDA_CHECK(cudaGetLastError());
     return B2_OK;
 }

@@ -99,3 +99,56 @@ class GBOPEngine(object):
                 "done": ((meta >> 16) & 1).astype(bool), "leaf": ((meta >> 17) & 1).astype(bool),
                 "reward": self.reward[tree, :n].cpu().numpy(), "lower": self.lower[tree, :n].cpu().numpy(),
                 "obs": self.obs[tree, :n].cpu().numpy()}
+
+
+class GBOPDEngine(object):
+    """n_trees independent GBOP-D decisions per launch (GraphBasedPlanner, one warp per decision)."""
+
+    def __init__(self, n_trees, n_actions, budget, gamma, mdp, accuracy=1e-2, sampling_timeout=100, device="cuda",
+                 queue_factor=256):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.n_trees, self.n_actions = int(n_trees), int(n_actions)
+        self.tables = FiniteTables(mdp, self.device)
+        S = self.n_states = self.tables.n_states
+        T = np.asarray(mdp.transition, dtype=np.int64)
+        # reverse transitions (the potential parents of every state), ascending and unique
+        pairs = np.unique(np.stack([T.reshape(-1), np.repeat(np.arange(S), self.n_actions)], axis=1), axis=0)
+        ptr = np.zeros(S + 1, dtype=np.int32)
+        np.add.at(ptr, pairs[:, 0] + 1, 1)
+        self.rev_ptr = torch.as_tensor(np.cumsum(ptr).astype(np.int32), device=self.device)
+        self.rev_idx = torch.as_tensor(pairs[:, 1].astype(np.int32), device=self.device)
+        self.timeout = int(sampling_timeout)
+        gamma = float(gamma)
+        self.queue_capacity = int(queue_factor) * S
+        self.cfg = _lib.GBOPDConfig(self.n_trees, self.n_actions, int(budget) // self.n_actions, self.timeout, self.timeout,
+                                    self.queue_capacity, gamma, 1 / (1 - gamma), float(accuracy), self.tables.struct(),
+                                    self.rev_ptr.data_ptr(), self.rev_idx.data_ptr())
+        self.lower = torch.empty((self.n_trees, S), dtype=torch.float64, device=self.device)
+        self.upper = torch.empty((self.n_trees, S), dtype=torch.float64, device=self.device)
+        self.flags = torch.empty((self.n_trees, S), dtype=torch.uint8, device=self.device)
+        self.queue = torch.empty((self.n_trees, self.queue_capacity), dtype=torch.int32, device=self.device)
+        self.rng = torch.empty((self.n_trees, _lib.PCG64_STATE_WORDS), dtype=torch.int64, device=self.device)
+        self.plan_buf = torch.empty((self.n_trees, self.timeout), dtype=torch.int8, device=self.device)
+        self.result = torch.empty((self.n_trees, _lib.OPD_RESULT_WORDS), dtype=torch.int32, device=self.device)
+
+    def plan(self, root_states, rng_words):
+        self.rng.copy_(self.torch.from_numpy(np.ascontiguousarray(rng_words).view(np.int64)))
+        _lib.check(self.lib.b2_gbopd_plan(self.cfg, _lib.ptr(root_states), _lib.ptr(self.lower), _lib.ptr(self.upper),
+                                          _lib.ptr(self.flags), _lib.ptr(self.queue), _lib.ptr(self.rng),
+                                          _lib.ptr(self.plan_buf), _lib.ptr(self.result), _lib.current_stream()))
+
+    def finish(self):
+        res = self.result.cpu().numpy()
+        if (res[:, 7] != 0).any():
+            raise _lib.B2Error("GBOP-D backup queue overflow: raise queue_factor")
+        plans_dev = self.plan_buf.cpu().numpy()
+        return [plans_dev[i, :res[i, 5]].astype(int).tolist() for i in range(self.n_trees)], res, \
+            self.rng.cpu().numpy().view(np.uint64)
+
+    def nodes(self, tree=0):
+        fl = self.flags[tree].cpu().numpy()
+        lo, up = self.lower[tree].cpu().numpy(), self.upper[tree].cpu().numpy()
+        return {int(s): dict(lower=float(lo[s]), upper=float(up[s]), expanded=bool(fl[s] & 2)) for s in np.nonzero(fl & 1)[0]}

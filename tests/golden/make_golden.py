@@ -313,6 +313,24 @@ def main():
                    "leaf_lower_sum": float(sum(l.value_lower for l in pl.leaves))}
     out["gbopt"] = gb
 
+    # ---------------- GBOP-D (graph-based OPD, graph_based.py): legacy 4-tuple step like OLOP ----------------
+    from rl_agents.agents.tree_search.graph_based import GraphBasedPlannerAgent
+    gd = {}
+    for key, (bud, gam, acc, seed_) in {"large1_b500_g0.9_acc0": (500, 0.9, 0, 0), "large1_b1500_g0.8_acc0": (1500, 0.8, 0, 2),
+                                        "large1_b500_g0.9_default": (500, 0.9, None, 0)}.items():
+        cfg = {"budget": bud, "gamma": gam}
+        if acc is not None:
+            cfg["accuracy"] = acc
+        agent = GraphBasedPlannerAgent(envs.LegacyStepEnv(finite()), cfg)
+        agent.seed(seed_)
+        plan = agent.plan(0)
+        pl = agent.planner
+        gd[key] = {"budget": bud, "gamma": gam, "accuracy": agent.config["accuracy"], "seed": seed_,
+                   "sampling_timeout": agent.config["sampling_timeout"], "plan": [int(a) for a in plan],
+                   "nodes": {str(k): [float(n.value_lower), float(n.value_upper), bool(n.children)]
+                             for k, n in pl.nodes.items()}}
+    out["gbopd"] = gd
+
     # ---------------- OLOP (KL) on finite ----------------
     ol = {}
     kl_cfg = {"budget": 200, "gamma": 0.9, "continuation_type": "uniform",

@@ -80,3 +80,46 @@ def test_gbopt_agent_plugin_surface():
     agent.seed(g["seed"])
     assert agent.plan(0) == g["plan"]
     assert agent.config["prune_suboptimal_leaves"] is True and agent.config["accuracy"] == 0
+
+
+# ------------------------------------------------------------------ GBOP-D (graph_based.py) ----
+@pytest.mark.parametrize("key", sorted(G["gbopd"]))
+def test_gbopd_matches_the_reference_and_the_oracle(key):
+    """accuracy = 0: plan, node set and both bounds of every node equal the UNMODIFIED reference's (the fixed
+    point does not depend on the order in which the reference's parent SETS are iterated); default accuracy: equal
+    to the oracle restatement (parents in ascending state id), the reference's plan, its bounds within `accuracy`."""
+    import torch
+    from rl_agents_b200.engine.gbop import GBOPDEngine
+    from rl_agents_b200.engine.mcts import pcg64_words
+    g = G["gbopd"][key]
+    eng = GBOPDEngine(1, 5, g["budget"], g["gamma"], mdp(), g["accuracy"], g["sampling_timeout"])
+    rng = np_random(g["seed"])
+    eng.plan(torch.tensor([0], dtype=torch.int32, device="cuda"), pcg64_words(rng).reshape(1, -1))
+    plans, res, words = eng.finish()
+    nodes = eng.nodes(0)
+    ref = {int(k): v for k, v in g["nodes"].items()}
+    assert plans[0] == g["plan"] and set(nodes) == set(ref)
+    assert all(nodes[s]["expanded"] == ref[s][2] for s in ref)
+    if g["accuracy"] == 0:
+        assert all(nodes[s]["lower"] == ref[s][0] and nodes[s]["upper"] == ref[s][1] for s in ref)
+    else:
+        assert all(abs(nodes[s]["lower"] - ref[s][0]) <= 10 * g["accuracy"] and
+                   abs(nodes[s]["upper"] - ref[s][1]) <= 10 * g["accuracy"] for s in ref)
+    orng = np_random(g["seed"])
+    env = oenvs.LegacyStepEnv(oenvs.FiniteMDPLite(M["large1_T"], M["large1_R"], M["large1_term"]))
+    plan, onodes = planners.graph_based_plan(env, 0, g["budget"], g["gamma"], orng, g["accuracy"], g["sampling_timeout"])
+    assert plans[0] == plan and nodes == onodes
+    from rl_agents_b200.engine.mcts import set_pcg64_words
+    set_pcg64_words(rng, words[0])
+    assert rng.bit_generator.state["state"] == orng.bit_generator.state["state"]     # same RNG consumption
+
+
+def test_gbopd_agent_plugin_surface():
+    from rl_agents_b200.agents.tree_search.graph_based import GraphBasedPlannerAgent
+    from rl_agents_b200.envs import FiniteMDPEnv
+    g = G["gbopd"]["large1_b500_g0.9_default"]
+    agent = GraphBasedPlannerAgent(FiniteMDPEnv(M["large1_T"], M["large1_R"], M["large1_term"]),
+                                   {"budget": g["budget"], "gamma": g["gamma"]})
+    agent.seed(g["seed"])
+    assert agent.plan(0) == g["plan"]
+    assert agent.config["accuracy"] == 1e-2 and agent.config["sampling_timeout"] == 100

@@ -307,3 +307,16 @@ def test_drop_oracle_matches_the_reference_goldens():
         assert plan == g["plan"], key
         assert t.parent == g["tree"]["parent"] and t.action == g["tree"]["action"] and t.count == g["tree"]["count"]
         assert t.lower == g["tree"]["lower"] and t.upper == g["tree"]["upper"]
+
+
+def test_graph_based_planner_gbopd():
+    """oracle.planners.graph_based_plan against the unmodified GraphBasedPlanner (legacy 4-tuple env shim): exact
+    for accuracy = 0, same plan / bounds within the accuracy for the default (the reference iterates parent sets)."""
+    for key, g in G["gbopd"].items():
+        plan, nodes = planners.graph_based_plan(envs.LegacyStepEnv(finite()), 0, g["budget"], g["gamma"], np_random(g["seed"]),
+                                                g["accuracy"], g["sampling_timeout"])
+        ref = {int(k): v for k, v in g["nodes"].items()}
+        assert plan == g["plan"] and set(nodes) == set(ref), key
+        tol = 0.0 if g["accuracy"] == 0 else 10 * g["accuracy"]
+        assert all(abs(nodes[s]["lower"] - ref[s][0]) <= tol and abs(nodes[s]["upper"] - ref[s][1]) <= tol and
+                   nodes[s]["expanded"] == ref[s][2] for s in ref), key
