@@ -783,13 +783,14 @@ def other_paths(a, dev, world, rank):
 
 def single_decision_latency(a, dev, reps=5):
     """ONE C2 decision (what agent.plan() does under scripts/experiments.py) at a time: the strict one-CTA
-    kernel and the wavefront kernel (b2_opd_plan_wave) at a few widths, plus one budget-1e6 decision.
+    kernel, the speculative strict kernel (b2_opd_plan_spec, same tree) and the wavefront kernel
+    (b2_opd_plan_wave) at a few widths, plus one budget-1e6 decision.
     CUDA-event median over `reps` launches per scene; quality of each width against the strict tree
     (root action agreement, gap of the root value_lower) on the same scenes."""
     import numpy as np
     import torch
     from rl_agents_b200 import _lib
-    from rl_agents_b200.engine.opd import OPDEngine, OPDWaveEngine
+    from rl_agents_b200.engine.opd import OPDEngine, OPDSpeculativeEngine, OPDWaveEngine
     from rl_agents_b200.envs.highway_lite import make_scene
     scenes = [torch.tensor(make_scene(s), dtype=torch.int32, device=dev) for s in range(4)]
     n_exp = a.budget // N_ACTIONS
@@ -817,6 +818,20 @@ def single_decision_latency(a, dev, reps=5):
         strict.append((plans[0][0], float(eng.lower[0, 0].item())))
     rows.append({"mode": "strict (reference order, one CTA)", "ms": ms, "expansions_per_s": n_exp / (ms * 1e-3)})
     del eng
+    # the same strict tree, bit for bit, searched by the whole GPU (b2_opd_plan_spec)
+    for width in (64, 256):
+        eng = OPDSpeculativeEngine(_lib.ENV_HIGHWAY, N_ACTIONS, a.budget, a.gamma, width, device=dev)
+        ms = float(np.median([med_ms(lambda: eng.plan(s)) for s in scenes]))
+        same, waves = 0, []
+        for s, (act, low) in zip(scenes, strict):
+            eng.plan(s)
+            plans, res = eng.finish([np.random.default_rng(0)])
+            same += int(plans[0][0] == act and float(eng.lower[0, 0].item()) == low)
+            waves.append(int(res[0, 7]))
+        rows.append({"mode": "speculative strict (reference order, whole GPU)", "candidates": width, "ms": ms,
+                     "expansions_per_s": n_exp / (ms * 1e-3), "waves": float(np.mean(waves)),
+                     "identical_root_action_and_value_vs_strict": same / float(len(scenes))})
+        del eng
     for width in (16, 64, 128):
         eng = OPDWaveEngine(_lib.ENV_HIGHWAY, N_ACTIONS, a.budget, a.gamma, width, device=dev)
         ms = float(np.median([med_ms(lambda: eng.plan(s)) for s in scenes]))

@@ -247,6 +247,17 @@ int64_t b2_opd_wave_workspace_bytes(const b2_opd_wave_config* cfg);
 int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* root_state, const b2_opd_tree* tree,
                      void* workspace, int8_t* plan, int32_t* result, void* stream);
 
+/* Speculative strict search: the reference's own one-leaf-per-iteration order (deterministic.py:106-114) -- the
+ * tree is bit-identical with b2_opd_plan / width 1 -- searched by the whole GPU.  Per wave the `width` best
+ * frontier leaves (value_upper descending, node id ascending) are simulated on every SM unless already cached,
+ * and the longest prefix the strict order would have expanded is committed.  Same config struct (width in
+ * 1..256, n_models = 0, node_capacity <= 24576); tree->state is an ARENA of b2_opd_spec_arena_slots(cfg)
+ * states (a node's state is not at its own index); result as for b2_opd_plan_wave. */
+int64_t b2_opd_spec_workspace_bytes(const b2_opd_wave_config* cfg);
+int64_t b2_opd_spec_arena_slots(const b2_opd_wave_config* cfg);
+int b2_opd_plan_spec(const b2_opd_wave_config* cfg, const int32_t* root_state, const b2_opd_tree* tree,
+                     void* workspace, int8_t* plan, int32_t* result, void* stream);
+
 /* ------------------------------------------------------------------------
  * GBOP-T -- rl_agents/agents/tree_search/state_aware.py (StateAwarePlanner), deterministic finite MDPs:
  * OPD whose leaf bounds share one value table per STATE (:66-68), tightened by a breadth-first backup through

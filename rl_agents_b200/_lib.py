@@ -145,6 +145,10 @@ EXPORTS = {
     "b2_opd_wave_workspace_bytes": (c_int64, [ctypes.POINTER(OPDWaveConfig)]),
     "b2_opd_plan_wave": (c_int, [ctypes.POINTER(OPDWaveConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
+    "b2_opd_spec_workspace_bytes": (c_int64, [ctypes.POINTER(OPDWaveConfig)]),
+    "b2_opd_spec_arena_slots": (c_int64, [ctypes.POINTER(OPDWaveConfig)]),
+    "b2_opd_plan_spec": (c_int, [ctypes.POINTER(OPDWaveConfig), c_void_p, ctypes.POINTER(OPDTree), c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "b2_gbop_workspace_bytes": (c_int64, [ctypes.POINTER(GBOPConfig)]),
     "b2_gbop_plan": (c_int, [ctypes.POINTER(GBOPConfig), c_void_p, ctypes.POINTER(GBOPTree), c_void_p, c_void_p,
                              c_void_p, c_void_p]),

@@ -64,6 +64,13 @@ struct Args {
     int32_t* wave_flags;   // joint mode: done | avail << 8 | reward-out-of-range << 16, per (child, model)
     DistScratch* dscr;     // distributed selection (trees larger than one shared-memory tile)
     int2* cta_cnt;         // [grid] per-CTA (taken-by-threshold, equal-to-threshold) counts
+    // speculative strict search (opd_spec_kernel)
+    int32_t* work_slot;    // [width * n_actions] arena slot of every transition of the current wave
+    int32_t* cand;         // [width] the wave's candidate leaves, id order
+    int32_t* spec_base;    // [node_capacity] first arena slot of a leaf's cached children, -1: not simulated yet
+    int32_t* state_slot;   // [node_capacity] arena slot holding the node's own state
+    double* spec_reward;   // [arena slots] reward of the cached transition
+    int32_t* spec_flags;   // [arena slots] action | done << 16 | reward-out-of-range << 17 | avail << 24
     int8_t* plan;
     int32_t* result;
 };
@@ -390,8 +397,10 @@ __device__ int select_dist(const Args& a, SelShared& sh, unsigned long long* ske
 }
 
 // CTA 0: choose this wave's leaves and lay out their children.  Returns the number of children (0: done).
+// `sel_out` / `do_layout`: the speculative kernel takes the chosen leaves (id order) in its own array and lays the
+// wave out itself; it then returns k.
 __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* skeys, int n_nodes, int n_expanded,
-                           int staged_nodes, long long* prof) {
+                           int staged_nodes, long long* prof, int32_t* sel_out = nullptr, bool do_layout = true) {
     const int tid = threadIdx.x;
     long long t0 = clock64();
     const int remaining = a.cfg.n_expansions - n_expanded;
@@ -518,7 +527,7 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
         slot ^= 1;
         need_eq = k - c;
     }
-    int32_t* sel = a.exp_order + n_expanded;     // the wave's leaves, id order (doubles as the expansion record)
+    int32_t* sel = sel_out ? sel_out : a.exp_order + n_expanded;     // the wave's leaves, id order (doubles as the expansion record)
     int run_sel = 0, run_eq = 0;
     for (int t = 0; t < n_tiles; ++t) {
         const int n = n_tiles == 1 ? n0 : stage(t);
@@ -550,6 +559,7 @@ __device__ int select_wave(const Args& a, SelShared& sh, unsigned long long* ske
     }
     __syncthreads();
     if (tid == 0) prof[2] += clock64() - t0;
+    if (!do_layout) return k;
     return layout_wave(a, sh, skeys, resident, n_nodes, n_expanded, k, slot, prof);
 }
 
@@ -637,6 +647,66 @@ __device__ __forceinline__ void finalize_joint_children(const Args& a, int total
         a.keys[c] = up;
         if (bad) a.ctl->error = 1;
         atomicMax(&a.ctl->max_depth, d);
+    }
+}
+
+// CTA 0, once the search is over: counts and bounds bottom-up, wave by wave in reverse, then the greedy plan.
+__device__ void finish_tree(const Args& a, long long tp) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    Control* ctl = a.ctl;
+    const b2_opd_tree& tr = a.tree;
+    // ------------------------------------------------------------------ bottom-up pass, reverse wave order
+    const volatile Control* vc = ctl;
+    const int n_waves = vc->n_waves, n_exp = vc->n_expanded, n_nodes = vc->n_nodes;
+    for (int w = n_waves - 1; w >= 0; --w) {
+        const int b = a.wave_start[w], e = a.wave_start[w + 1];
+        for (int j = b + tid; j < e; j += THREADS) {
+            const int p = a.exp_order[j];
+            const int fc = tr.first_child[p];
+            const int n = (tr.meta[p] >> 8) & 0xff;
+            double lo = -INFINITY, up = -INFINITY;
+            int desc = 0;
+            for (int q = 0; q < n; ++q) {
+                const double l2 = ld_cg(tr.lower + fc + q), u2 = ld_cg(tr.upper + fc + q);
+                lo = l2 > lo ? l2 : lo;
+                up = u2 > up ? u2 : up;
+                desc += ld_cg(tr.count + fc + q) - 1;
+            }
+            tr.lower[p] = lo;                       // backup_to_root (:74-79)
+            tr.upper[p] = up;
+            tr.count[p] = (p == 0 ? 1 : 2) + desc;  // :64-65
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (tid >= 32) return;
+    // get_plan (abstract.py:143-156) on value_lower; a tie is broken on the host with the planner RNG
+    int node = 0, len = 0, tie_node = -1;
+    while (true) {
+        const int fc = ld_cg(tr.first_child + node);
+        if (fc < 0) break;
+        const int n = (ld_cg(tr.meta + node) >> 8) & 0xff;
+        const double lo = lane < n ? ld_cg(tr.lower + fc + lane) : -INFINITY;
+        const double m = warp_max_f64(lo);
+        const unsigned eq = __ballot_sync(0xffffffffu, lane < n && lo == m);
+        if (__popc(eq) > 1) { tie_node = node; break; }
+        const int c = fc + __ffs(eq) - 1;
+        if (lane == 0 && len < a.cfg.plan_capacity) a.plan[len] = (int8_t)(ld_cg(tr.meta + c) & 0xff);
+        ++len;
+        node = c;
+    }
+    if (lane == 0) {
+        int32_t* res = a.result;
+        res[0] = n_nodes;
+        res[1] = n_nodes - n_exp;
+        res[2] = vc->max_depth;
+        res[3] = vc->term_exp;
+        res[4] = vc->error;
+        res[5] = len;
+        res[6] = tie_node;
+        res[7] = n_waves;
+        ctl->prof[6] += clock64() - tp;
+        for (int i = 0; i < 8; ++i) res[8 + i] = (int32_t)(i == 7 ? ctl->prof[i] : ctl->prof[i] >> 8);   // 256-cycle units
     }
 }
 
@@ -801,66 +871,316 @@ __global__ void __launch_bounds__(THREADS, 1) opd_wave_kernel(Args a) {
         if (*(volatile int*)&ctl->error) break;
     }
     if (blockIdx.x != 0) return;
-    // ------------------------------------------------------------------ bottom-up pass, reverse wave order
-    const volatile Control* vc = ctl;
-    const int n_waves = vc->n_waves, n_exp = vc->n_expanded, n_nodes = vc->n_nodes;
-    for (int w = n_waves - 1; w >= 0; --w) {
-        const int b = a.wave_start[w], e = a.wave_start[w + 1];
-        for (int j = b + tid; j < e; j += THREADS) {
-            const int p = a.exp_order[j];
-            const int fc = tr.first_child[p];
-            const int n = (tr.meta[p] >> 8) & 0xff;
-            double lo = -INFINITY, up = -INFINITY;
-            int desc = 0;
-            for (int q = 0; q < n; ++q) {
-                const double l2 = ld_cg(tr.lower + fc + q), u2 = ld_cg(tr.upper + fc + q);
-                lo = l2 > lo ? l2 : lo;
-                up = u2 > up ? u2 : up;
-                desc += ld_cg(tr.count + fc + q) - 1;
-            }
-            tr.lower[p] = lo;                       // backup_to_root (:74-79)
-            tr.upper[p] = up;
-            tr.count[p] = (p == 0 ? 1 : 2) + desc;  // :64-65
-        }
-        __threadfence();
-        __syncthreads();
-    }
-    if (tid >= 32) return;
-    // get_plan (abstract.py:143-156) on value_lower; a tie is broken on the host with the planner RNG
-    int node = 0, len = 0, tie_node = -1;
-    while (true) {
-        const int fc = ld_cg(tr.first_child + node);
-        if (fc < 0) break;
-        const int n = (ld_cg(tr.meta + node) >> 8) & 0xff;
-        const double lo = lane < n ? ld_cg(tr.lower + fc + lane) : -INFINITY;
-        const double m = warp_max_f64(lo);
-        const unsigned eq = __ballot_sync(0xffffffffu, lane < n && lo == m);
-        if (__popc(eq) > 1) { tie_node = node; break; }
-        const int c = fc + __ffs(eq) - 1;
-        if (lane == 0 && len < a.cfg.plan_capacity) a.plan[len] = (int8_t)(ld_cg(tr.meta + c) & 0xff);
-        ++len;
-        node = c;
-    }
-    if (lane == 0) {
-        int32_t* res = a.result;
-        res[0] = n_nodes;
-        res[1] = n_nodes - n_exp;
-        res[2] = vc->max_depth;
-        res[3] = vc->term_exp;
-        res[4] = vc->error;
-        res[5] = len;
-        res[6] = tie_node;
-        res[7] = n_waves;
-        ctl->prof[6] += clock64() - tp;
-        for (int i = 0; i < 8; ++i) res[8 + i] = (int32_t)(i == 7 ? ctl->prof[i] : ctl->prof[i] >> 8);   // 256-cycle units
-    }
+    finish_tree(a, tp);
 }
+
+// ---------------------------------------------------------------------------
+// Speculative strict search (b2_opd_plan_spec): the reference's one-leaf-per-iteration order
+// (deterministic.py:106-114), bit for bit, without paying one dependent env transition per expansion.
+//
+// Per wave CTA 0 takes the K best frontier leaves in the reference's arg-max order (value_upper descending, node
+// id ascending); every SM simulates the children of those that have not been simulated yet into an arena
+// (a leaf is simulated at most once: the results stay cached until the leaf is expanded).  The strict search
+// would expand candidate j next iff no child created by candidates 0..j-1 has a larger value_upper than j (a
+// child that ties loses: it has the larger id), so CTA 0 commits the longest such prefix -- children get their
+// final ids by a prefix sum, in the strict order -- and the rest stays speculative.  Candidate 0 always
+// commits, so the search advances every wave; gamma < 1 makes children's bounds tighter than their parents'
+// and the prefix long.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int ordered_actions(const Args& a, int mask, int* acts) {
+    int q = 0;
+    for (int i = 0; i < MAX_BRANCH; ++i) {
+        int act;
+        if (a.cfg.env_kind == B2_ENV_HIGHWAY) {
+            if (i >= 5) break;
+            const int order[5] = {hw::A_IDLE, hw::A_LEFT, hw::A_RIGHT, hw::A_FASTER, hw::A_SLOWER};
+            act = order[i];
+        } else if (a.cfg.env_kind == B2_ENV_INTERSECTION) {
+            if (i >= 3) break;
+            const int order[3] = {il::A_IDLE, il::A_FASTER, il::A_SLOWER};
+            act = order[i];
+        } else {
+            if (i >= a.cfg.n_actions) break;
+            act = i;
+        }
+        if (mask & (1 << act)) acts[q++] = act;
+    }
+    return q;
+}
+
+struct SpecShared {
+    unsigned long long key[THREADS];    // candidates in strict order
+    int leaf[THREADS];
+    unsigned long long wmax[WARPS];
+    int first_fail;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) opd_spec_kernel(Args a) {
+    extern __shared__ unsigned long long skeys[];
+    __shared__ SelShared sh;
+    __shared__ SpecShared sp;
+    __shared__ float hw_scratch[GROUPS][hw::SCRATCH_FLOATS];
+    __shared__ int s_nodes, s_expanded, s_slots;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, li = tid & 15;
+    const unsigned n_ctas = gridDim.x;
+    Control* ctl = a.ctl;
+    const b2_opd_tree& tr = a.tree;
+    const int kind = a.cfg.env_kind;
+    static_assert(hw::WORDS == il::WORDS, "one arena stride for both scene kinds");
+    const int words = kind == B2_ENV_FINITE ? 1 : hw::WORDS;
+    for (int i = blockIdx.x * THREADS + tid; i < a.cfg.node_capacity; i += THREADS * (int)n_ctas) a.spec_base[i] = -1;
+    if (blockIdx.x == 0) {
+        int avail = 0;
+        if (kind == B2_ENV_INTERSECTION) avail = il::avail_mask(a.root_state[129]);
+        else if (kind == B2_ENV_HIGHWAY) avail = hw::avail_mask(__int_as_float(a.root_state[hw::V]), a.root_state[8 * hw::V + 1]);
+        else avail = (1 << a.cfg.n_actions) - 1;
+        for (int i = tid; i < words; i += THREADS) tr.state[i] = a.root_state[i];       // arena slot 0
+        if (tid == 0) {
+            tr.parent[0] = -1; tr.first_child[0] = -1; tr.depth[0] = 0; tr.count[0] = 1;
+            tr.meta[0] = 0xff | (avail << 24);
+            tr.reward[0] = 0.0; tr.lower[0] = 0.0; tr.upper[0] = 0.0;
+            a.state_slot[0] = 0;
+            skeys[0] = sortable(0.0);
+            s_nodes = 1; s_expanded = 0; s_slots = 1;
+        }
+    }
+    grid_barrier(ctl, n_ctas);
+    long long tp = clock64();
+    auto lap = [&](int slot) {
+        if (blockIdx.x == 0 && tid == 0) { const long long t1 = clock64(); ctl->prof[slot] += t1 - tp; tp = t1; }
+    };
+    int k = 0;
+    while (true) {
+        // ---------------------------------------------------------------- candidates + transitions to simulate
+        if (blockIdx.x == 0) {
+            const int nn = s_nodes, ne = s_expanded, slots0 = s_slots;
+            __syncthreads();
+            k = select_wave(a, sh, skeys, nn, ne, nn, ctl->prof, a.cand, false);
+            if (k > 0) {
+                // strict order: key descending, id ascending (the candidates arrive in id order)
+                long long t0 = clock64();
+                int my_leaf = 0;
+                unsigned long long my_key = 0;
+                if (tid < k) { my_leaf = a.cand[tid]; my_key = skeys[my_leaf]; sp.key[tid] = my_key; }
+                __syncthreads();
+                int rank = 0;
+                if (tid < k) {
+                    for (int i = 0; i < k; ++i) {
+                        const unsigned long long ki = sp.key[i];
+                        rank += (ki > my_key || (ki == my_key && i < tid)) ? 1 : 0;
+                    }
+                }
+                __syncthreads();
+                if (tid < k) { sp.key[rank] = my_key; sp.leaf[rank] = my_leaf; }
+                __syncthreads();
+                int leaf = 0, n = 0, need = 0, acts[MAX_BRANCH];
+                if (tid < k) {
+                    leaf = sp.leaf[tid];
+                    const int meta = tr.meta[leaf];
+                    const int mask = kind != B2_ENV_FINITE ? (meta >> 24) & 0x1f : (1 << a.cfg.n_actions) - 1;
+                    n = ordered_actions(a, mask, acts);
+                    need = a.spec_base[leaf] < 0 ? n : 0;
+                }
+                int e1, e2, total, t2;
+                block_scan2(need, 0, sh, e1, e2, total, t2);
+                if (need > 0) {
+                    a.spec_base[leaf] = slots0 + e1;
+                    for (int q = 0; q < n; ++q) {
+                        a.work[e1 + q] = leaf | (acts[q] << 28);
+                        a.work_slot[e1 + q] = slots0 + e1 + q;
+                    }
+                }
+                if (tid == 0) {
+                    ctl->wave_children = total;
+                    s_slots = slots0 + total;
+                    ctl->prof[2] += clock64() - t0;
+                }
+            } else if (tid == 0) {
+                ctl->stop = 1;
+            }
+            if (tid == 0) tp = clock64();
+        }
+        grid_barrier(ctl, n_ctas);
+        lap(3);
+        if (*(volatile int*)&ctl->stop) break;
+        // ---------------------------------------------------------------- simulate (all CTAs)
+        const int total = *(volatile int*)&ctl->wave_children;
+        if (kind == B2_ENV_FINITE) {
+            const b2_finite_mdp& m = a.cfg.mdp;
+            for (int w = blockIdx.x * THREADS + tid; w < total; w += THREADS * (int)n_ctas) {
+                const int item = __ldcg(a.work + w), slot = __ldcg(a.work_slot + w);
+                const int leaf = item & 0x0fffffff, action = (item >> 28) & 7;
+                const int s = ld_cg(tr.state + __ldcg(a.state_slot + leaf));
+                const double r = m.reward[(int64_t)s * m.n_actions + action];
+                tr.state[slot] = m.transition[(int64_t)s * m.n_actions + action];
+                a.spec_reward[slot] = r;
+                a.spec_flags[slot] = action | (m.terminal[s] != 0 ? 1 << 16 : 0) | ((r >= 0.0 && r <= 1.0) ? 0 : 1 << 17);
+            }
+        } else {
+            const int warp_global = warp * (int)n_ctas + (int)blockIdx.x;
+            const int n_warps = WARPS * (int)n_ctas;
+            for (int w0 = 2 * warp_global; w0 < total; w0 += 2 * n_warps) {
+                const int w_raw = w0 + ((tid >> 4) & 1);
+                const bool real = w_raw < total;
+                const int w = real ? w_raw : w0;
+                const int item = __ldcg(a.work + w), slot = __ldcg(a.work_slot + w);
+                const int leaf = item & 0x0fffffff;
+                const int32_t* src = tr.state + (int64_t)__ldcg(a.state_slot + leaf) * hw::WORDS;
+                int32_t* dst = tr.state + (int64_t)slot * hw::WORDS;
+                bool term, trunc;
+                float r;
+                int avail, action;
+                if (kind == B2_ENV_HIGHWAY) {
+                    action = real ? (item >> 28) & 7 : hw::A_IDLE;
+                    hw::Lane L;
+                    int t, si;
+                    load_state_cg(src, li, L, t, si);
+                    r = hw::step(L, li, t, si, action, term, trunc, 0xffffffffu, hw_scratch[tid >> 4]);
+                    const float ego_y = __shfl_sync(0xffffffffu, L.y, 0, 16);
+                    avail = hw::avail_mask(ego_y, si);
+                    if (real) hw::store_state(dst, li, L, t, si);
+                } else {
+                    action = real ? (item >> 28) & 7 : il::A_IDLE;
+                    il::Lane L;
+                    il::Globals g;
+                    il::load_state<true>(src, li, L, g);
+                    r = il::step(L, li, g, action, term, trunc, 0xffffffffu);
+                    avail = il::avail_mask(g.si);
+                    if (real) il::store_state(dst, li, L, g);
+                }
+                if (real && li == 0) {
+                    const double rd = (double)r;
+                    a.spec_reward[slot] = rd;
+                    a.spec_flags[slot] = action | (term ? 1 << 16 : 0) | ((rd >= 0.0 && rd <= 1.0) ? 0 : 1 << 17) | (avail << 24);
+                }
+            }
+        }
+        lap(4);
+        grid_barrier(ctl, n_ctas);
+        lap(5);
+        // ---------------------------------------------------------------- commit the strict prefix (CTA 0)
+        if (blockIdx.x == 0) {
+            const int nn = s_nodes, ne = s_expanded;
+            const int remaining = a.cfg.n_expansions - ne;
+            int leaf = 0, n = 0, base = 0, d = 0, flags[MAX_BRANCH];
+            double rew[MAX_BRANCH], lo[MAX_BRANCH], up[MAX_BRANCH];
+            unsigned long long m = 0;                         // largest child key of this candidate
+            if (tid < k) {
+                leaf = sp.leaf[tid];
+                base = a.spec_base[leaf];
+                const int meta = tr.meta[leaf];
+                n = __popc(kind != B2_ENV_FINITE ? (meta >> 24) & 0x1f : (1 << a.cfg.n_actions) - 1);
+                d = tr.depth[leaf] + 1;
+                const double lowl = tr.lower[leaf], gp = a.cfg.gamma_pow[d - 1], gpd = a.cfg.gamma_pow_div[d],
+                             tb = a.cfg.terminal_bonus[d];
+                for (int q = 0; q < MAX_BRANCH; ++q) {
+                    if (q >= n) break;
+                    rew[q] = __ldcg(a.spec_reward + base + q);
+                    flags[q] = __ldcg(a.spec_flags + base + q);
+                    double l2 = lowl + gp * rew[q];           // DeterministicNode.update (:52-63)
+                    double u2 = l2 + gpd;
+                    if (flags[q] & (1 << 16)) { l2 = l2 + tb; u2 = l2; }
+                    lo[q] = l2; up[q] = u2;
+                    const unsigned long long uk = sortable(u2);
+                    m = uk > m ? uk : m;
+                }
+            }
+            // exclusive prefix maximum of m over the strict order
+            unsigned long long inc = m;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long x = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc = x > inc ? x : inc;
+            }
+            unsigned long long exc = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) exc = 0;
+            if (lane == 31) sp.wmax[warp] = inc;
+            if (tid == 0) sp.first_fail = k;
+            __syncthreads();
+            for (int i = 0; i < warp; ++i) exc = sp.wmax[i] > exc ? sp.wmax[i] : exc;
+            if (tid < k && exc > sp.key[tid]) atomicMin(&sp.first_fail, tid);
+            __syncthreads();
+            const int n_commit = min(sp.first_fail, remaining);
+            const bool mine = tid < n_commit;
+            int ec, e2, total_c, t2;
+            block_scan2(mine ? n : 0, 0, sh, ec, e2, total_c, t2);
+            int term = 0;
+            if (mine) {
+                const int c0 = nn + ec;
+                const int meta = tr.meta[leaf];
+                tr.first_child[leaf] = c0;
+                tr.meta[leaf] = meta | (n << 8);
+                skeys[leaf] = ABSENT;
+                a.exp_order[ne + tid] = leaf;
+                term = (meta >> 16) & 1;
+                for (int q = 0; q < MAX_BRANCH; ++q) {
+                    if (q >= n) break;
+                    const int c = c0 + q;
+                    tr.parent[c] = leaf;
+                    tr.first_child[c] = -1;
+                    tr.depth[c] = d;
+                    tr.count[c] = 2;
+                    tr.meta[c] = flags[q] & ~(1 << 17);
+                    tr.reward[c] = rew[q];
+                    tr.lower[c] = lo[q];
+                    tr.upper[c] = up[q];
+                    a.state_slot[c] = base + q;
+                    skeys[c] = sortable(up[q]);
+                    if (flags[q] & (1 << 17)) ctl->error = 1;          // :46-47
+                }
+                atomicMax(&ctl->max_depth, d);
+            }
+            term = block_sum(term, sh.red, 0);
+            if (tid == 0) {
+                ctl->term_exp += term;
+                a.wave_start[ctl->n_waves] = ne;
+                ctl->n_waves += 1;
+                a.wave_start[ctl->n_waves] = ne + n_commit;
+                ctl->n_nodes = nn + total_c;
+                ctl->n_expanded = ne + n_commit;
+                s_nodes = nn + total_c;
+                s_expanded = ne + n_commit;
+            }
+            __syncthreads();
+            lap(0);
+            if (ctl->error) {
+                if (tid == 0) ctl->stop = 1;
+            }
+        }
+    }
+    if (blockIdx.x != 0) return;
+    finish_tree(a, tp);
+}
+
 
 static int64_t align_up(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 struct Layout {
     int64_t ctl, keys, exp_order, wave_start, work, lowerv, wave_up, wave_flags, dscr, cta_cnt, total;
 };
+
+struct SpecLayout {
+    int64_t ctl, exp_order, wave_start, work, work_slot, cand, spec_base, state_slot, spec_reward, spec_flags, total;
+};
+
+static int64_t spec_arena_slots(const b2_opd_wave_config* c) { return 1 + (int64_t)c->node_capacity * c->n_actions; }
+
+static SpecLayout make_spec_layout(const b2_opd_wave_config* c) {
+    SpecLayout l;
+    const int64_t wa = (int64_t)c->width * c->n_actions, slots = spec_arena_slots(c);
+    l.ctl = 0;
+    l.exp_order = align_up(sizeof(Control));
+    l.wave_start = l.exp_order + align_up((int64_t)c->n_expansions * 4 + 4);
+    l.work = l.wave_start + align_up(((int64_t)c->n_expansions + 2) * 4);
+    l.work_slot = l.work + align_up(wa * 4 + 4);
+    l.cand = l.work_slot + align_up(wa * 4 + 4);
+    l.spec_base = l.cand + align_up((int64_t)c->width * 4 + 4);
+    l.state_slot = l.spec_base + align_up((int64_t)c->node_capacity * 4);
+    l.spec_reward = l.state_slot + align_up((int64_t)c->node_capacity * 4);
+    l.spec_flags = l.spec_reward + align_up(slots * 8);
+    l.total = l.spec_flags + align_up(slots * 4);
+    return l;
+}
 
 static Layout make_layout(const b2_opd_wave_config* c) {
     Layout l;
@@ -945,6 +1265,72 @@ extern "C" int b2_opd_plan_wave(const b2_opd_wave_config* cfg, const int32_t* ro
     if (grid > wave::THREADS) grid = wave::THREADS;      // the distributed selection scans the CTA table with one block
     void* params[] = {&a};
     B2_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)wave::opd_wave_kernel, dim3(grid), dim3(wave::THREADS), params,
+                                              smem, stream));
+    return B2_OK;
+}
+
+static bool spec_config_ok(const b2_opd_wave_config* cfg) {
+    return cfg && cfg->n_expansions >= 0 && cfg->width > 0 && cfg->width <= wave::THREADS && cfg->n_actions > 0 &&
+           cfg->n_actions <= wave::MAX_BRANCH && cfg->n_models == 0 && cfg->node_capacity <= wave::STAGE_CAP &&
+           (int64_t)cfg->node_capacity >= 1 + (int64_t)cfg->n_expansions * cfg->n_actions;
+}
+
+extern "C" int64_t b2_opd_spec_workspace_bytes(const b2_opd_wave_config* cfg) {
+    if (!spec_config_ok(cfg)) return -1;
+    return wave::make_spec_layout(cfg).total;
+}
+
+extern "C" int64_t b2_opd_spec_arena_slots(const b2_opd_wave_config* cfg) {
+    if (!spec_config_ok(cfg)) return -1;
+    return wave::spec_arena_slots(cfg);
+}
+
+extern "C" int b2_opd_plan_spec(const b2_opd_wave_config* cfg, const int32_t* root_state, const b2_opd_tree* tree,
+                                void* workspace, int8_t* plan, int32_t* result, void* stream_) {
+    B2_REQUIRE(cfg && root_state && tree && workspace && plan && result, "null pointer");
+    B2_REQUIRE(spec_config_ok(cfg),
+               "speculative search: width in 1..256, n_actions in 1..8, n_models = 0, node_capacity in "
+               "[1 + n_expansions * n_actions, 24576]");
+    B2_REQUIRE(cfg->plan_capacity >= 1, "plan_capacity too small");
+    B2_REQUIRE(cfg->gamma_pow && cfg->gamma_pow_div && cfg->terminal_bonus, "gamma tables missing");
+    if (cfg->env_kind == B2_ENV_FINITE) {
+        B2_REQUIRE(cfg->mdp.transition && cfg->mdp.reward && cfg->mdp.terminal, "finite MDP tables missing");
+        B2_REQUIRE(cfg->mdp.n_actions == cfg->n_actions, "mdp.n_actions != n_actions");
+    } else if (cfg->env_kind == B2_ENV_HIGHWAY) {
+        B2_REQUIRE(cfg->n_actions == B2_HW_ACTIONS, "HighwayLite has 5 actions");
+    } else if (cfg->env_kind == B2_ENV_INTERSECTION) {
+        B2_REQUIRE(cfg->n_actions == B2_IL_ACTIONS, "IntersectionLite has 3 actions");
+    } else {
+        set_error("unknown env_kind %d", cfg->env_kind);
+        return B2_ERR_INVALID;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const wave::SpecLayout l = wave::make_spec_layout(cfg);
+    char* ws = (char*)workspace;
+    wave::Args a;
+    memset(&a, 0, sizeof(a));
+    a.cfg = *cfg; a.tree = *tree; a.root_state = root_state;
+    a.ctl = (wave::Control*)(ws + l.ctl);
+    a.exp_order = (int32_t*)(ws + l.exp_order);
+    a.wave_start = (int32_t*)(ws + l.wave_start);
+    a.work = (int32_t*)(ws + l.work);
+    a.work_slot = (int32_t*)(ws + l.work_slot);
+    a.cand = (int32_t*)(ws + l.cand);
+    a.spec_base = (int32_t*)(ws + l.spec_base);
+    a.state_slot = (int32_t*)(ws + l.state_slot);
+    a.spec_reward = (double*)(ws + l.spec_reward);
+    a.spec_flags = (int32_t*)(ws + l.spec_flags);
+    a.plan = plan; a.result = result;
+    B2_CUDA_CHECK(cudaMemsetAsync(a.ctl, 0, sizeof(wave::Control), stream));
+    const size_t smem = (size_t)cfg->node_capacity * 8;
+    B2_CUDA_CHECK(cudaFuncSetAttribute(wave::opd_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    B2_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave::opd_spec_kernel, wave::THREADS, smem));
+    B2_REQUIRE(per_sm >= 1, "speculative kernel does not fit on an SM");
+    int grid = sm_count();
+    if (cfg->max_ctas > 0 && cfg->max_ctas < grid) grid = cfg->max_ctas;
+    void* params[] = {&a};
+    B2_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)wave::opd_spec_kernel, dim3(grid), dim3(wave::THREADS), params,
                                               smem, stream));
     return B2_OK;
 }

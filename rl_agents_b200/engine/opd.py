@@ -160,3 +160,39 @@ class OPDWaveEngine(OPDEngine):
     @property
     def n_waves(self):
         return int(self.result[0, 7].item())
+
+
+class OPDSpeculativeEngine(OPDEngine):
+    """ONE OPD decision in the reference's strict best-first order (deterministic.py:106-114), searched by the
+    whole GPU (b2_opd_plan_spec): per wave the `width` best frontier leaves are simulated speculatively (once:
+    results stay cached until the leaf is expanded) and the prefix the strict order would have taken is
+    committed.  The tree is bit-identical with OPDEngine's; `state` is an arena (a node's scene is not at its
+    index).  Trees up to 24576 nodes."""
+
+    def __init__(self, env_kind, n_actions, budget, gamma, width=64, terminal_reward=0.0, mdp=None, device="cuda",
+                 max_ctas=0):
+        super(OPDSpeculativeEngine, self).__init__(env_kind, 1, n_actions, budget, gamma, terminal_reward, mdp, device)
+        self.width = int(width)
+        torch = self.torch
+        self.wcfg = _lib.OPDWaveConfig(env_kind, self.n_actions, self.n_expansions, self.capacity, self.plan_capacity,
+                                       self.width, int(max_ctas), 0, self.gamma_pow.data_ptr(),
+                                       self.gamma_pow_div.data_ptr(), self.terminal_bonus.data_ptr(),
+                                       self.tables.struct() if self.tables else _lib.FiniteMDP())
+        ws = self.lib.b2_opd_spec_workspace_bytes(self.wcfg)
+        slots = self.lib.b2_opd_spec_arena_slots(self.wcfg)
+        if ws < 0 or slots < 0:
+            raise _lib.B2Error("unsupported speculative OPD configuration (width <= 256, tree <= 24576 nodes)")
+        sshape = (1, int(slots)) if env_kind == _lib.ENV_FINITE else (1, int(slots), _lib.HW_STATE_WORDS)
+        self.state = torch.empty(sshape, dtype=torch.int32, device=self.device)
+        self.tree = _lib.OPDTree(*[t.data_ptr() for t in (self.parent, self.first_child, self.depth, self.count,
+                                                          self.meta, self.reward, self.lower, self.upper, self.state)])
+        self.workspace = torch.empty(int(ws), dtype=torch.uint8, device=self.device)
+
+    def plan(self, root_state):
+        assert root_state.dtype == self.torch.int32 and root_state.is_cuda and root_state.is_contiguous()
+        _lib.check(self.lib.b2_opd_plan_spec(self.wcfg, _lib.ptr(root_state), self.tree, _lib.ptr(self.workspace),
+                                             _lib.ptr(self.plan_buf), _lib.ptr(self.result), _lib.current_stream()))
+
+    @property
+    def n_waves(self):
+        return int(self.result[0, 7].item())
