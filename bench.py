@@ -338,7 +338,7 @@ def run_reference(a):
               "each) back to back; %d of %d timed steps done = %d expansions in %.1f s; 1 step = 1/%d of %d plan()s per "
               "process" % (workers, cores, os.cpu_count() or 0, a.budget, n_exp, done_steps, steps, total, dt, steps,
                            plans_per_worker))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "OPD leaf-expansions/sec on highway-v0 (HighwayLite)", "value": value,
         "unit": "expansions/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "steps_done": done_steps,
         "ms_per_step": 1e3 * dt / max(done_steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -349,7 +349,7 @@ def run_reference(a):
                          "single_process_value": (n_exp / med) if med else None,
                          "plans_timed": len(plan_times)},
         "e2e": {"value": value, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 # ----------------------------------------------------------------------------
@@ -538,7 +538,7 @@ def run_b200(a):
         except Exception as e:      # the C oracle is optional test infrastructure
             out["cpu_port_c"] = {"unavailable": str(e)[:200]}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -865,8 +865,27 @@ def single_decision_latency(a, dev, reps=5):
             "rows": rows, "budget_1e6_decision": big}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line: libraries that write to fd 1 on their own (NCCL prints its version banner
+    there under NCCL_DEBUG=VERSION) are pointed at stderr; emit() writes the line to the real stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
     a = parse()
+    claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
