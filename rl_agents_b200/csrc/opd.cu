@@ -545,7 +545,9 @@ __global__ void __launch_bounds__(128) highway_step_kernel(int32_t* states, cons
 }
 
 // Exhaustive check of hw::div_const against the IEEE division for the two constant divisors of the spec:
-// every fp32 mantissa, both signs, exponents -60 .. +60 (quotients stay normal).  Counts mismatching bit patterns.
+// every fp32 mantissa, both signs, exponents -60 .. +60 (quotients stay normal); and of hw::div_fast against the
+// `/` operator on 2^33 operand pairs (every numerator mantissa x 1024 hashed divisors of either sign, both
+// magnitudes in 2^-40 .. 2^40).  Counts mismatching bit patterns.
 __global__ void const_division_selftest_kernel(unsigned long long* mismatches) {
     const unsigned m = blockIdx.x * blockDim.x + threadIdx.x;       // mantissa, 2^23 threads
     unsigned long long bad = 0;
@@ -556,6 +558,16 @@ __global__ void const_division_selftest_kernel(unsigned long long* mismatches) {
             const float c = x / hw::HALF_LENGTH, d = hw::div_const(x, hw::HALF_LENGTH, hw::RCP_HALF_LENGTH);
             bad += (__float_as_uint(a) != __float_as_uint(b)) + (__float_as_uint(c) != __float_as_uint(d));
         }
+    }
+    unsigned long long h = 0x9e3779b97f4a7c15ull * (m + 1);
+    for (int it = 0; it < 1024; ++it) {
+        h ^= h >> 30; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 27; h *= 0x94d049bb133111ebull; h ^= h >> 31;
+        const unsigned ea = 127 - 40 + (unsigned)(h >> 56) % 81u, eb = 127 - 40 + (unsigned)((h >> 48) & 0xff) % 81u;
+        const float x = __uint_as_float((((unsigned)(h >> 47) & 1u) << 31) | (ea << 23) | m);
+        float y = __uint_as_float((((unsigned)(h >> 46) & 1u) << 31) | (eb << 23) | ((unsigned)h & 0x7fffffu));
+        asm volatile("" : "+f"(y));      // opaque: the reference quotient below is the compiler's own division
+        const float q = x / y, f = hw::div_fast(x, y);
+        bad += __float_as_uint(q) != __float_as_uint(f);
     }
     if (bad) atomicAdd(mismatches, bad);
 }
