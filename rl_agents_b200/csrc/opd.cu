@@ -354,7 +354,9 @@ __global__ void __launch_bounds__(MT_THREADS, B2_MT_MIN_BLOCKS) opd_highway_mult
     const int n_local = min(MT_TREES, a.cfg.n_trees - tree0);
     // the warp's own tree
     const int my_tree = tree0 + warp;
-    const bool owner = warp < n_local;
+    // warp-uniform conditions are taken through votes: ptxas then knows the branches cannot split the warp and drops the
+    // divergence guards (BRA.DIV / WARPSYNC) around every collective in the regions they control
+    const bool owner = __all_sync(0xffffffffu, warp < n_local);
     const int64_t my_nb = (int64_t)my_tree * a.cfg.node_capacity;
     char* my_ws = a.workspace + (int64_t)(owner ? my_tree : tree0) * a.lay.ws_bytes_per_tree;
     Tournament T;
@@ -374,7 +376,8 @@ __global__ void __launch_bounds__(MT_THREADS, B2_MT_MIN_BLOCKS) opd_highway_mult
     __syncthreads();
     for (int it = 0; it < a.cfg.n_expansions; ++it) {
         // ---- phase 1: every warp selects the leaf of its own tree ----
-        if (!ms.dead[warp]) {
+        const bool alive = __all_sync(0xffffffffu, ms.dead[warp] == 0);
+        if (alive) {
             const int leaf = T.select(lane);
             if (lane == 0) {
                 Shared& sh = ms.sh[warp];
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(MT_THREADS, B2_MT_MIN_BLOCKS) opd_highway_mult
         for (int u = 0; u < MT_TREES; ++u) offs[u + 1] = offs[u] + ms.n[u];
         const int total = offs[MT_TREES];
         for (int base = 0; base < total; base += MT_GROUPS) {
-            if (base + 2 * warp >= total) continue;          // neither group of this warp has work
+            if (__all_sync(0xffffffffu, base + 2 * warp >= total)) continue;   // neither group of this warp has work (vote: provably warp-uniform branch)
             const int slot = base + grp;
             const bool real = slot < total;
             int tr = 0;
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(MT_THREADS, B2_MT_MIN_BLOCKS) opd_highway_mult
         }
         __syncthreads();
         // ---- phase 3: every warp commits its own tree ----
-        if (!ms.dead[warp]) {
+        if (alive) {
             Shared& sh = ms.sh[warp];
             const int n = ms.n[warp], c0 = ms.n_nodes[warp];
             commit_expansion(a, T, sh, my_nb, sh.leaf, c0, n, ms.n_exp[warp], my_exp_order, lane);
