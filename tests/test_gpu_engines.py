@@ -392,11 +392,11 @@ def test_opd_highway_batch_vs_oracle():
         assert np.array_equal(d["lower"], np.array(t.lower)) and np.array_equal(d["upper"], np.array(t.upper))
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_opd_highway_packed_batch_equals_single_tree_search(kernel):
     """>= 16 trees take a batch kernel (0: 8 trees per CTA, children of different trees share the
-    simulation slots; 1: one tree per warp); every tree must equal the one-tree-per-CTA search
-    and the oracle."""
+    simulation slots, block barriers between the phases; 1: one tree per warp; 2: 8 trees per CTA as a dataflow over
+    a shared work ring, no block barriers); every tree must equal the one-tree-per-CTA search and the oracle."""
     seeds = list(range(40, 59))          # 19 trees: full CTAs + a partial one
     words = [oenvs.make_highway_state(s).pack() for s in seeds]
     eng, plans, res = run_opd_highway(words, 150, 0.8, kernel=kernel)
@@ -619,13 +619,15 @@ def test_edge_cases_small_budgets_and_argument_validation():
         m.plan(torch.zeros(1, dtype=torch.int32, device="cuda"), pcg64_words(np_random(0)).reshape(1, -1))
 
 
-def test_opd_highway_c2_full_size_batch_vs_c_oracle():
-    """C2 at full size, many decisions: 24 scenes x budget 10 000 through the batch kernel, every node
-    array of every tree bit-identical with the C oracle (itself pinned to the reference's golden tree)."""
+@pytest.mark.parametrize("kernel", [0, 2])
+def test_opd_highway_c2_full_size_batch_vs_c_oracle(kernel):
+    """C2 at full size, many decisions: 24 scenes x budget 10 000 through the batch kernels (barrier and dataflow
+    variants), every node array of every tree bit-identical with the C oracle (itself pinned to the reference's
+    golden tree)."""
     from oracle import c_oracle
     seeds = list(range(500, 524))
     words = [oenvs.make_highway_state(s).pack() for s in seeds]
-    eng, plans, res = run_opd_highway(words, 10000, 0.8)
+    eng, plans, res = run_opd_highway(words, 10000, 0.8, kernel=kernel)
     for i, w in enumerate(words):
         t = c_oracle.opd_plan(w, 10000, 0.8)
         d = eng.tree_dict(i)
