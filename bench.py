@@ -486,17 +486,22 @@ def run_b200(a):
         pass
 
     ncu = None      # static evidence from the committed ncu capture of this kernel (not measured in this run)
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_opd_highway_multi_ncu_summary.json")) as f:
-            summ = json.load(f)
-        ncu = {"source": "profiles/r01_opd_highway_multi_ncu_summary.json",
-               "ipc_per_sm": float(summ["sm__inst_executed.avg.per_cycle_elapsed"][0]),
-               "issue_slots_busy_pct": float(summ["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
-               "alu_pipe_pct": float(summ["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"][0]),
-               "fma_pipe_pct": float(summ["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"][0]),
-               "dram_pct": float(summ["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"][0])}
-    except Exception:
-        pass
+    for name in ("r02d_opd_multi_ncu_summary.json", "r02b_opd_multi_ncu_summary.json", "r01_opd_highway_multi_ncu_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                summ = json.load(f)
+            summ = summ.get("opd_highway_multi_kernel", summ)      # newer summaries are keyed by kernel name
+            inst = float(summ["smsp__inst_executed.sum"][0]) if "smsp__inst_executed.sum" in summ else None
+            ncu = {"source": "profiles/" + name,
+                   "ipc_per_sm": float(summ["sm__inst_executed.avg.per_cycle_elapsed"][0]),
+                   "issue_slots_busy_pct": float(summ["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+                   "alu_pipe_pct": float(summ["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"][0]),
+                   "fma_pipe_pct": float(summ["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"][0]),
+                   "dram_pct": float(summ["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"][0]),
+                   "warp_instructions_in_capture": inst}
+            break
+        except Exception:
+            continue
     out = {
         "metric": "OPD leaf-expansions/sec on highway-v0 (HighwayLite)", "value": value, "unit": "expansions/s",
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
