@@ -170,7 +170,9 @@ typedef struct b2_opd_config {
     int32_t plan_capacity;  /* per tree, >= n_expansions + 1                 */
     int32_t keys_in_smem;   /* 1: frontier keys in shared memory when they fit */
     int32_t reserved;       /* HighwayLite batch kernel: 0 default (8 trees per CTA, packed
-                               slots), 1 one tree per warp                   */
+                               slots, block barriers between the phases), 1 one tree per warp,
+                               2 8 trees per CTA as a dataflow over a work ring in shared
+                               memory (no block barriers); identical trees, 0 is fastest */
     double terminal_reward; /* config["terminal_reward"] (:60-63)            */
     const double* gamma_pow;     /* [n_expansions+2] gamma**d   (host floats) */
     const double* gamma_pow_div; /* [n_expansions+2] gamma**d / (1 - gamma)   */
