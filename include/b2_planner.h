@@ -61,6 +61,18 @@ typedef struct b2_finite_mdp {
 int b2_highway_step(int32_t* states, const int32_t* actions, float* reward, int32_t* flags,
                     int32_t* avail_mask, int32_t n_envs, void* stream);
 
+/* ValueIterationAgent on HighwayLite scenes, batched: per scene, the time-to-collision grid MDP that
+ * `env.unwrapped.to_finite_mdp()` hands the reference's agent (rl_agents/agents/dynamic_programming/
+ * value_iteration.py:17,32; docs/HIGHWAY_LITE_SPEC.md section 9: 3 speeds x 4 lanes x 10 s = 120 states, 5 actions,
+ * deterministic) is built and the agent's fixed-point iteration (value_iteration.py:42-73, incl. the np.allclose early
+ * exit that returns the previous iterate) is run by one warp in shared memory.
+ * states [n_envs,136] i32; q_out [n_envs,120,5] f64 or NULL; action_out [n_envs] i32 = argmax_a Q[state] (:35);
+ * mdp_state_out [n_envs] i32 (the scene's cell, `mdp.state`) or NULL; sweeps_out [n_envs] i32 or NULL. */
+#define B2_TTC_STATES 120
+int b2_highway_ttc_vi(const int32_t* states, int32_t n_envs, double gamma, int32_t iterations, double rtol,
+                      double atol, double* q_out, int32_t* action_out, int32_t* mdp_state_out, int32_t* sweeps_out,
+                      void* stream);
+
 /* The same for IntersectionLite (BASELINE config C5's env model): 3 actions (0 SLOWER, 1 IDLE, 2 FASTER),
  * states [n_envs, 136] words, avail_mask in the NEW state. */
 int b2_intersection_step(int32_t* states, const int32_t* actions, float* reward, int32_t* flags,

@@ -487,6 +487,86 @@ def highway_step(state, action):
     return f32(r), ego_crashed, s.t >= DURATION
 
 
+# ---------------------------------------------------------------------------
+# TTC-grid MDP of a HighwayLite scene (docs/HIGHWAY_LITE_SPEC.md section 9): what
+# `env.unwrapped.to_finite_mdp()` hands to ValueIterationAgent
+# (rl_agents/agents/dynamic_programming/value_iteration.py:17,32).  It follows the
+# published algorithm of highway-env's `envs/common/finite_mdp.py` (not under
+# /root/reference, not installed: restated from its documented behaviour --
+# `compute_ttc_grid(env, time_quantization=1., horizon=10.)` is how the reference
+# itself calls it, agents/dynamic_programming/graphics.py:46).  Literal loops.
+# ---------------------------------------------------------------------------
+TTC_SPEEDS = (20.0, 25.0, 30.0)
+TTC_HORIZON = 10.0
+TTC_TIME_QUANTIZATION = 1.0
+TTC_COLLISION_REWARD, TTC_RIGHT_LANE_REWARD, TTC_HIGH_SPEED_REWARD, TTC_LANE_CHANGE_REWARD = -1.0, 0.1, 0.4, 0.0
+
+
+def highway_ttc_grid(state):
+    """grid[h, lane, t] in {0, 0.5, 1}: cost of being on `lane` in t seconds when driving at TTC_SPEEDS[h]."""
+    n_t = int(TTC_HORIZON / TTC_TIME_QUANTIZATION)
+    grid = np.zeros((len(TTC_SPEEDS), N_LANES, n_t))
+    margin = float(LENGTH) / 2 + float(LENGTH) / 2
+    for h, ego_speed in enumerate(TTC_SPEEDS):
+        for k in range(1, V_SLOTS):
+            if not (state.flags[k] & 1):
+                continue
+            if ego_speed == float(state.v[k]):
+                continue
+            c = cos_p(np.array([f32(state.h[k] - state.h[0])], dtype=f32))[0]      # fp32, the step's own polynomial
+            projected = float(state.v[k]) * float(c)
+            diff = ego_speed - projected
+            nz = diff if abs(diff) > 0.01 else (0.01 if diff >= 0 else -0.01)
+            lane = int(np.clip(np.rint(state.y[k] / f32(4.0)), 0, N_LANES - 1))
+            for m, cost in ((0.0, 1.0), (-margin, 0.5), (margin, 0.5)):
+                distance = (float(state.x[k]) - float(state.x[0])) + m
+                ttc = distance / nz
+                if ttc < 0:
+                    continue
+                for t in (int(ttc / TTC_TIME_QUANTIZATION), int(np.ceil(ttc / TTC_TIME_QUANTIZATION))):
+                    if 0 <= t < n_t:
+                        grid[h, lane, t] = max(grid[h, lane, t], cost)
+    return grid
+
+
+def highway_finite_mdp(state):
+    """Deterministic MDP over (speed index, lane, time) cells: transition [S, A] int, reward [S, A], terminal [S]."""
+    grid = highway_ttc_grid(state)
+    n_h, n_l, n_t = grid.shape
+    n_s = grid.size
+
+    def cell(h, i, j):
+        return (min(max(h, 0), n_h - 1) * n_l + min(max(i, 0), n_l - 1)) * n_t + min(max(j, 0), n_t - 1)
+
+    transition = np.zeros((n_s, N_ACTIONS), dtype=np.int64)
+    reward = np.zeros((n_s, N_ACTIONS))
+    terminal = np.zeros(n_s, dtype=bool)
+    action_reward = (TTC_LANE_CHANGE_REWARD, 0.0, TTC_LANE_CHANGE_REWARD, 0.0, 0.0)
+    for h in range(n_h):
+        for i in range(n_l):
+            for j in range(n_t):
+                s = (h * n_l + i) * n_t + j
+                state_reward = (TTC_COLLISION_REWARD * grid[h, i, j] + TTC_RIGHT_LANE_REWARD * (i / max(n_l - 1, 1))
+                                + TTC_HIGH_SPEED_REWARD * (h / max(n_h - 1, 1)))
+                terminal[s] = grid[h, i, j] == 1 or j == n_t - 1
+                for a in range(N_ACTIONS):
+                    nh, ni = h, i
+                    if a == A_LEFT:
+                        ni = i - 1
+                    elif a == A_RIGHT:
+                        ni = i + 1
+                    elif a == A_FASTER and j == 0:
+                        nh = h + 1
+                    elif a == A_SLOWER and j == 0:
+                        nh = h - 1
+                    transition[s, a] = cell(nh, ni, j + 1)
+                    reward[s, a] = state_reward + action_reward[a]
+    ego_lane = int(np.clip(np.rint(state.y[0] / f32(4.0)), 0, N_LANES - 1))
+    mdp = _MDP("deterministic", transition, reward, terminal, state=cell(int(state.speed_index), ego_lane, 0))
+    mdp.original_shape = grid.shape
+    return mdp
+
+
 class HighwayLite(object):
     """gym-like wrapper the reference planners can deepcopy and step."""
 
@@ -506,6 +586,9 @@ class HighwayLite(object):
 
     def get_available_actions(self):
         return highway_available_actions(self.state)
+
+    def to_finite_mdp(self):
+        return highway_finite_mdp(self.state)
 
     def __deepcopy__(self, memo):
         return HighwayLite(self.state.copy())

@@ -37,6 +37,14 @@ class ValueIterationAgent(AbstractAgent):
     def default_config(cls):
         return {"gamma": 1.0, "iterations": 100}       # value_iteration.py:24-27
 
+    def _scene_words(self):
+        """The 136-word scene when the env is a HighwayLite scene model and the conversion may run on the device
+        (config["conversion"]: "device" (default) | "host"), else None."""
+        unwrapped = getattr(self.env, "unwrapped", self.env)
+        if getattr(unwrapped, "b2_env_kind", None) == "highway" and self.config.get("conversion", "device") == "device":
+            return unwrapped.words
+        return None
+
     # -- MDP hand-off ---------------------------------------------------------
     @staticmethod
     def is_finite_mdp(env):
@@ -57,6 +65,14 @@ class ValueIterationAgent(AbstractAgent):
     # -- solving ----------------------------------------------------------------
     def get_state_action_value(self):
         """Q of shape [S, A] (numpy, host copy of the device result)."""
+        words = self._scene_words()
+        if words is not None:
+            # HighwayLite scene: TTC-grid conversion + fixed point in one kernel (b2_highway_ttc_vi); self.mdp is the
+            # host statement of the same MDP (envs/highway_lite.py::ttc_finite_mdp), kept for plan_trajectory()
+            from rl_agents_b200.engine.ttc_vi import HighwayTTCVI
+            out = HighwayTTCVI(self.config["gamma"], self.config["iterations"]).solve(words.reshape(1, -1))
+            self.sweeps = int(out["sweeps"][0].item())
+            return out["q"][0].cpu().numpy()
         from rl_agents_b200.engine.vi import VIEngine
         mdp = self.mdp
         engine = VIEngine(mdp.mode, mdp.transition, mdp.reward, mdp.terminal, nxt=getattr(mdp, "next", None),

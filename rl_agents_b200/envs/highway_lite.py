@@ -61,6 +61,77 @@ def available_actions(words):
     return [a for a in _ORDER if mask[a]]
 
 
+# ---- time-to-collision grid MDP (docs/HIGHWAY_LITE_SPEC.md section 9) ----------------------------------------------
+TTC_SPEEDS = np.array([20.0, 25.0, 30.0])
+TTC_STEPS = 10                       # horizon 10 s / time quantization 1 s
+TTC_REWARDS = {"collision": -1.0, "right_lane": 0.1, "high_speed": 0.4, "lane_change": 0.0}
+_COS_C = np.array([-0.5, 1.0 / 24, -1.0 / 720, 1.0 / 40320, -1.0 / 3628800, 1.0 / 479001600]).astype(np.float32)
+
+
+def _cos_p(x):
+    """The spec's fp32 cosine polynomial (docs/HIGHWAY_LITE_SPEC.md section 3), one rounding per operation."""
+    half_pi = np.float32(1.5707963705062866)
+    x = np.minimum(np.maximum(x.astype(np.float32), -half_pi), half_pi)
+    z = x * x
+    acc = np.full_like(z, _COS_C[-1])
+    for c in _COS_C[-2::-1]:
+        acc = c + z * acc
+    return np.float32(1.0) + z * acc
+
+
+def ttc_grid(words):
+    """[3 speeds, 4 lanes, 10 s] costs in {0, 0.5, 1}, all (speed, vehicle, collision point) triples at once."""
+    words = np.asarray(words, dtype=np.int32)
+    f = words[:96].view(np.float32).reshape(6, V_SLOTS)
+    x, y, h, v = f[0], f[1], f[2], f[3]
+    others = np.flatnonzero((words[112:128] & 1) != 0)
+    others = others[others > 0]
+    grid = np.zeros((TTC_SPEEDS.size, N_LANES, TTC_STEPS))
+    if others.size == 0:
+        return grid
+    proj = v[others].astype(np.float64) * _cos_p(h[others] - h[0]).astype(np.float64)             # [K]
+    lane = np.clip(np.rint(y[others] / np.float32(4.0)), 0, N_LANES - 1).astype(np.int64)           # [K]
+    diff = TTC_SPEEDS[:, None] - proj[None, :]                                                      # [H, K]
+    nz = np.where(np.abs(diff) > 0.01, diff, np.where(diff >= 0, 0.01, -0.01))
+    offs = np.array([0.0, -5.0, 5.0])                          # collision points: centre, both bumpers (LENGTH/2 + LENGTH/2)
+    cost = np.array([1.0, 0.5, 0.5])
+    dist = (x[others].astype(np.float64) - np.float64(x[0]))[None, :, None] + offs[None, None, :]   # [1, K, P]
+    ttc = dist / nz[:, :, None]                                                                     # [H, K, P]
+    ok = (ttc >= 0) & (TTC_SPEEDS[:, None] != v[others].astype(np.float64)[None, :])[:, :, None]
+    ttc = np.where(ok, ttc, -1.0)
+    for t in (np.trunc(ttc), np.ceil(ttc)):
+        hh, kk, pp = np.nonzero(ok & (t >= 0) & (t < TTC_STEPS))
+        np.maximum.at(grid, (hh, lane[kk], t[hh, kk, pp].astype(np.int64)), cost[pp])
+    return grid
+
+
+def ttc_finite_mdp(words):
+    from rl_agents_b200.envs.finite_mdp import FiniteMDP
+    words = np.asarray(words, dtype=np.int32)
+    grid = ttc_grid(words)
+    n_h, n_l, n_t = grid.shape
+    hh, ii, jj = np.meshgrid(np.arange(n_h), np.arange(n_l), np.arange(n_t), indexing="ij")
+
+    def cell(a, b, c):
+        return (np.clip(a, 0, n_h - 1) * n_l + np.clip(b, 0, n_l - 1)) * n_t + np.clip(c, 0, n_t - 1)
+
+    first = jj == 0
+    nxt = [cell(hh, ii - 1, jj + 1), cell(hh, ii, jj + 1), cell(hh, ii + 1, jj + 1),
+           cell(hh + first, ii, jj + 1), cell(hh - first, ii, jj + 1)]            # LEFT, IDLE, RIGHT, FASTER, SLOWER
+    transition = np.stack([t.reshape(-1) for t in nxt], axis=1)
+    rw = TTC_REWARDS
+    state_reward = (rw["collision"] * grid + rw["right_lane"] * (ii / max(n_l - 1, 1))
+                    + rw["high_speed"] * (hh / max(n_h - 1, 1))).reshape(-1)
+    action_reward = np.array([rw["lane_change"], 0.0, rw["lane_change"], 0.0, 0.0])
+    reward = state_reward[:, None] + action_reward[None, :]
+    terminal = ((grid == 1) | (jj == n_t - 1)).reshape(-1)
+    y0 = words[16:17].view(np.float32)[0]
+    ego_lane = int(np.clip(np.rint(y0 / np.float32(4.0)), 0, N_LANES - 1))
+    mdp = FiniteMDP("deterministic", transition, reward, terminal, state=int(cell(int(words[129]), ego_lane, 0)))
+    mdp.original_shape = grid.shape
+    return mdp
+
+
 class HighwayLiteEnv(object):
     b2_env_kind = "highway"
 
@@ -94,6 +165,11 @@ class HighwayLiteEnv(object):
 
     def get_available_actions(self):
         return available_actions(self.words)
+
+    def to_finite_mdp(self):
+        """`env.unwrapped.to_finite_mdp()` of the reference's ValueIterationAgent (value_iteration.py:17,32): the
+        time-to-collision grid MDP of this scene (docs/HIGHWAY_LITE_SPEC.md section 9)."""
+        return ttc_finite_mdp(self.words)
 
     def assume_traffic(self, args):
         """Model variant for robust planning (`"models": [[{"method": "assume_traffic", "args": {...}}], ...]`):

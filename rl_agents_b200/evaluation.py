@@ -15,7 +15,8 @@ def _np_random(seed):
 
 
 def run_batched_episodes(planner, seeds, budget, gamma, max_steps=40, device="cuda", planner_seed=0, **kw):
-    """planner: "opd" | "mcts" | "olop".  Every episode: scene make_scene(seed), replanning at every
+    """planner: "opd" | "mcts" | "olop" | "vi" (ValueIterationAgent on the scenes' TTC-grid MDPs, `budget` = its
+    `iterations`).  Every episode: scene make_scene(seed), replanning at every
     step (receding_horizon 1, step_strategy reset -- the reference defaults), until crash or `max_steps`.
     Returns dict(returns, lengths, crashed, decision_ms)."""
     import torch
@@ -41,6 +42,9 @@ def run_batched_episodes(planner, seeds, budget, gamma, max_steps=40, device="cu
         ub = kw.get("upper_bound", {"type": "kullback-leibler", "time": "global", "threshold": "2*np.log(time)"})
         eng = OLOPEngine(_lib.ENV_HIGHWAY, n, 5, episodes, horizon, gamma, ub, kw.get("continuation_type", "uniform"),
                          device=dev)
+    elif planner == "vi":
+        from rl_agents_b200.engine.ttc_vi import HighwayTTCVI
+        eng = HighwayTTCVI(gamma, budget, device=dev)
     else:
         raise ValueError("unknown planner %r" % planner)
     returns = np.zeros(n)
@@ -58,6 +62,8 @@ def run_batched_episodes(planner, seeds, budget, gamma, max_steps=40, device="cu
         if planner == "opd":
             eng.plan(scenes)
             plans, _ = eng.finish(rngs)
+        elif planner == "vi":
+            plans = [[int(a)] for a in eng.solve(scenes, want_q=False)["action"].cpu().numpy()]
         else:
             eng.plan(scenes, np.stack([pcg64_words(g) for g in rngs]))
             plans, _, words = eng.finish()

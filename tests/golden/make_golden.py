@@ -387,7 +387,43 @@ def main():
     with open(os.path.join(HERE, "golden_highway.json"), "w") as f:
         json.dump(hw, f)
     print("highway done")
+    highway_vi()
+
+
+def highway_vi():
+    """ValueIterationAgent on HighwayLite scenes through `env.unwrapped.to_finite_mdp()` (value_iteration.py:17,32;
+    shipped config scripts/configs/HighwayEnv/agents/ValueIterationAgent/baseline.json: iterations 10, gamma 1):
+    the unmodified reference agent on the oracle's TTC-grid MDP of the scene -> tests/golden/golden_highway_vi.json."""
+    out = {"cases": []}
+    for seed in range(6):
+        env = envs.HighwayLite(seed=seed)
+        rng = np.random.default_rng(300 + seed)
+        for step in range(0, 13):
+            if step in (0, 3, 7, 12):
+                for cfg in ({"iterations": 10}, {"gamma": 0.9, "iterations": 100}):
+                    agent = ref_vi.ValueIterationAgent(env, dict(cfg))
+                    mdp = agent.mdp
+                    case = {"seed": seed, "step": step, "config": cfg, "words": env.state.pack().tolist(),
+                            "state": int(mdp.state), "shape": list(mdp.original_shape),
+                            "grid": envs.highway_ttc_grid(env.state).tolist(),
+                            "q": agent.state_action_value.tolist(), "act": int(agent.act(None))}
+                    if seed == 0 and step in (0, 7) and "gamma" not in cfg:
+                        case["transition"] = mdp.transition.tolist()
+                        case["reward"] = mdp.reward.tolist()
+                        case["terminal"] = [bool(x) for x in mdp.terminal]
+                    out["cases"].append(case)
+            avail = env.get_available_actions()
+            a = 1 if rng.uniform() < 0.5 else int(avail[rng.integers(len(avail))])
+            _, _, term_, _, _ = env.step(a)
+            if term_:
+                break
+    with open(os.path.join(HERE, "golden_highway_vi.json"), "w") as f:
+        json.dump(out, f)
+    print("highway VI done:", len(out["cases"]), "cases")
 
 
 if __name__ == "__main__":
-    main()
+    if "--only-highway-vi" in sys.argv:
+        highway_vi()
+    else:
+        main()
