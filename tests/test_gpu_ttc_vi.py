@@ -6,7 +6,7 @@ import pytest
 
 from oracle import envs as oenvs
 from oracle import planners
-from tests.util import load_golden
+from tests.util import load_golden, ttc_edge_scenes
 
 pytestmark = pytest.mark.gpu
 V = load_golden("golden_highway_vi.json")
@@ -33,6 +33,7 @@ def test_ttc_vi_kernel_matches_the_oracle_on_many_scenes():
     words = [oenvs.make_highway_state(s).pack() for s in range(100, 164)]
     for steps in H["traces"].values():
         words += [np.array(s["state"], dtype=np.int32) for s in steps]
+    words += ttc_edge_scenes()
     for gamma, iterations in ((1.0, 10), (0.95, 3), (0.8, 100), (1.0, 0)):
         out = solve(words, gamma, iterations)
         for i, w in enumerate(words):

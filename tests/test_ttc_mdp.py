@@ -5,7 +5,7 @@ import numpy as np
 
 from oracle import envs as oenvs
 from oracle import planners
-from tests.util import load_golden
+from tests.util import load_golden, ttc_edge_scenes
 
 V = load_golden("golden_highway_vi.json")
 H = load_golden("golden_highway.json")
@@ -48,7 +48,8 @@ def test_product_host_ttc_mdp_equals_the_oracle():
     words = [np.array(c["words"], dtype=np.int32) for c in V["cases"]]
     for steps in H["traces"].values():                                 # scenes in the middle of lane changes, crashes
         words += [np.array(s["state"], dtype=np.int32) for s in steps[::4]]
-    assert len(words) > 100
+    words += ttc_edge_scenes()
+    assert len(words) > 140
     for w in words:
         st = oenvs.HighwayLiteState.unpack(w)
         assert np.array_equal(ttc_grid(w), oenvs.highway_ttc_grid(st))

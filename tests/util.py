@@ -68,3 +68,36 @@ def canonical_tree(first_child, n_children, fields):
         order.extend(range(first_child[n], first_child[n] + n_children[n]) if n_children[n] > 0 else [])
         head += 1
     return [[int(n_children[i])] + [f[i] for f in fields] for i in order]
+
+
+def ttc_edge_scenes():
+    """HighwayLite scenes that exercise the corners of the TTC-grid conversion (docs/HIGHWAY_LITE_SPEC.md section 9):
+    absent slots, speeds equal to the grid speeds, integer times / zero distances, headings beyond the cosine clamp,
+    negative speeds, vehicles off the road or between lanes, all ego cells, relative speeds inside the +-0.01 guard."""
+    from oracle import envs as oenvs
+    out = []
+    rng = np.random.default_rng(7)
+    for s in range(40):
+        w = oenvs.make_highway_state(200 + s).pack()
+        f = w[:96].view(np.float32)
+        kind = s % 8
+        if kind == 0:
+            w[112 + rng.integers(1, 16, size=6)] = 0
+        elif kind == 1:
+            f[48 + 1:48 + 16] = np.float32(rng.choice([20.0, 25.0, 30.0], size=15))
+        elif kind == 2:
+            f[1:16] = f[0] + np.float32(rng.integers(-3, 4, size=15) * 5.0)
+        elif kind == 3:
+            f[32 + 1:32 + 16] = np.float32(rng.uniform(-2.0, 2.0, size=15))
+        elif kind == 4:
+            f[48 + 1:48 + 16] = np.float32(rng.uniform(-5.0, 45.0, size=15))
+        elif kind == 5:
+            f[16 + 1:16 + 16] = np.float32(rng.uniform(-6.0, 18.0, size=15))
+        elif kind == 6:
+            w[129] = int(rng.integers(0, 3))
+            f[16] = np.float32(rng.choice([0.0, 4.0, 8.0, 12.0, 2.0, 6.0, 10.0]))
+        else:
+            f[1:16] = f[0] + np.float32(rng.uniform(-400, 400, size=15))
+            f[48 + 1:48 + 16] = np.float32(f[48] + rng.uniform(-0.02, 0.02, size=15))
+        out.append(w)
+    return out
