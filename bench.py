@@ -783,6 +783,30 @@ def other_paths(a, dev, world, rank):
             "collective": None if world == 1 else "one all_reduce(MAX) of the [n_subtrees, 2] bounds"}
     except Exception as ex:
         out["opd_c5_subtree_sharded"] = {"error": repr(ex)[:300]}
+
+    # ---- ValueIterationAgent on highway scenes (shipped config: iterations 10, gamma 1): conversion to the TTC-grid
+    #      MDP + the agent's fixed point as ONE kernel over a batch of scenes resident in HBM (every rank the same batch;
+    #      rank 0's time).  value_iteration.py:29-35 does both on the host at every act(). ----
+    try:
+        from rl_agents_b200.engine.ttc_vi import HighwayTTCVI
+        n_sc = 1 << 18
+        base = np.stack([make_scene(s) for s in range(256)])
+        scenes = torch.from_numpy(np.tile(base, (n_sc // 256, 1))).to(dev)
+        eng = HighwayTTCVI(1.0, 10, device=dev)
+        res = {}
+
+        def run_ttc():
+            res["out"] = eng.solve(scenes, want_q=False)
+        ms = timed_ms(run_ttc, reps=3)
+        out["vi_highway_ttc"] = {
+            "workload": "ValueIterationAgent.act() on %d HighwayLite scenes: to_finite_mdp() (TTC grid, 120 states x 5 "
+                        "actions) + 10 sweeps of the fixed point per scene, fused (b2_highway_ttc_vi, one warp per scene)" % n_sc,
+            "ms_per_launch": ms, "decisions_per_s": n_sc / (ms * 1e-3),
+            "sweeps_mean": float(res["out"]["sweeps"].float().mean().item()),
+            "parity": "Q bit-identical with the unmodified reference agent (tests/test_gpu_ttc_vi.py)"}
+        del scenes
+    except Exception as ex:
+        out["vi_highway_ttc"] = {"error": repr(ex)[:300]}
     return out
 
 
