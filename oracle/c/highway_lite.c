@@ -199,3 +199,113 @@ float hl_step(hl_state* s, int action, int* flags_out) {
     *flags_out = (crashed0 ? 1 : 0) | (s->t >= HL_DURATION ? 2 : 0);
     return r;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * ValueIterationAgent on a HighwayLite scene (docs/HIGHWAY_LITE_SPEC.md section 9): the time-to-collision grid MDP of
+ * `env.unwrapped.to_finite_mdp()` and the reference agent's fixed point on it
+ * (rl_agents/agents/dynamic_programming/value_iteration.py:17,29-35,42-73).  Third statement, after
+ * oracle/envs.py::highway_finite_mdp (+ oracle/planners.py::value_iteration) and rl_agents_b200/csrc/ttc_vi.cu; explicit
+ * tables, literal loops.  TEST INFRASTRUCTURE.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define TTC_H 3
+#define TTC_T 10
+enum { A_LEFT = 0, A_IDLE = 1, A_RIGHT = 2, A_FASTER = 3, A_SLOWER = 4 };
+#define TTC_S (TTC_H * HL_LANES * TTC_T)
+#define TTC_A 5
+
+static int ttc_clip(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+static int ttc_cell(int h, int i, int j) { return (ttc_clip(h, TTC_H - 1) * HL_LANES + ttc_clip(i, HL_LANES - 1)) * TTC_T + ttc_clip(j, TTC_T - 1); }
+static int ttc_lane(float y) { return ttc_clip((int)rintf(y / 4.0f), HL_LANES - 1); }
+
+/* grid [3][4][10] of costs 0 / 0.5 / 1 */
+void hl_ttc_grid(const hl_state* s, double* grid) {
+    hl_init();
+    for (int c = 0; c < TTC_S; ++c) grid[c] = 0.0;
+    const double margin = (double)LENGTH / 2 + (double)LENGTH / 2;
+    const double points[3][2] = {{0.0, 1.0}, {-margin, 0.5}, {margin, 0.5}};
+    for (int h = 0; h < TTC_H; ++h) {
+        const double ego_speed = 20.0 + 5.0 * h;
+        for (int k = 1; k < HL_V; ++k) {
+            if (!(s->flags[k] & 1)) continue;
+            if (ego_speed == (double)s->v[k]) continue;
+            const float dh = s->h[k] - s->h[0];
+            const double projected = (double)s->v[k] * (double)cos_p(dh);
+            const double diff = ego_speed - projected;
+            const double nz = fabs(diff) > 0.01 ? diff : (diff >= 0 ? 0.01 : -0.01);
+            const int lane = ttc_lane(s->y[k]);
+            for (int p = 0; p < 3; ++p) {
+                const double distance = ((double)s->x[k] - (double)s->x[0]) + points[p][0];
+                const double ttc = distance / nz;
+                if (ttc < 0) continue;
+                const double tq[2] = {floor(ttc), ceil(ttc)};        /* int(ttc), int(ceil(ttc)) for ttc >= 0 */
+                for (int q = 0; q < 2; ++q) {
+                    if (tq[q] >= 0 && tq[q] < TTC_T) {
+                        double* g = &grid[(h * HL_LANES + lane) * TTC_T + (int)tq[q]];
+                        if (points[p][1] > *g) *g = points[p][1];
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* q_out [120][5]; returns the number of sweeps; *state = mdp.state, *action = argmax_a Q[state] */
+int hl_ttc_value_iteration(const int32_t* words, double gamma, int iterations, double rtol, double atol, double* q_out,
+                           int32_t* state, int32_t* action) {
+    const hl_state* s = (const hl_state*)words;
+    static double grid[TTC_S], reward[TTC_S][TTC_A], q[TTC_S][TTC_A], nq[TTC_S][TTC_A], v[TTC_S];
+    static int transition[TTC_S][TTC_A], terminal[TTC_S];
+    hl_ttc_grid(s, grid);
+    const double action_reward[TTC_A] = {0.0, 0.0, 0.0, 0.0, 0.0};      /* lane_change_reward = 0 */
+    for (int h = 0; h < TTC_H; ++h)
+        for (int i = 0; i < HL_LANES; ++i)
+            for (int j = 0; j < TTC_T; ++j) {
+                const int c = (h * HL_LANES + i) * TTC_T + j;
+                const double state_reward = (-1.0 * grid[c] + 0.1 * ((double)i / (HL_LANES - 1))) + 0.4 * ((double)h / (TTC_H - 1));
+                terminal[c] = grid[c] == 1.0 || j == TTC_T - 1;
+                for (int a = 0; a < TTC_A; ++a) {
+                    int nh = h, ni = i;
+                    if (a == A_LEFT) ni = i - 1;
+                    else if (a == A_RIGHT) ni = i + 1;
+                    else if (a == A_FASTER && j == 0) nh = h + 1;
+                    else if (a == A_SLOWER && j == 0) nh = h - 1;
+                    transition[c][a] = ttc_cell(nh, ni, j + 1);
+                    reward[c][a] = state_reward + action_reward[a];
+                    q[c][a] = 0.0;
+                }
+            }
+    int sweeps = 0;
+    for (int it = 0; it < iterations; ++it) {
+        ++sweeps;
+        for (int c = 0; c < TTC_S; ++c) {
+            double m = q[c][0];
+            for (int a = 1; a < TTC_A; ++a) m = q[c][a] > m ? q[c][a] : m;
+            v[c] = m;
+        }
+        int close = 1;
+        for (int c = 0; c < TTC_S; ++c)
+            for (int a = 0; a < TTC_A; ++a) {
+                const double next_v = terminal[c] ? 0.0 : v[transition[c][a]];
+                nq[c][a] = reward[c][a] + gamma * next_v;
+                if (!(fabs(q[c][a] - nq[c][a]) <= atol + rtol * fabs(nq[c][a]))) close = 0;
+            }
+        if (close) break;                               /* the previous iterate is returned (:71-72) */
+        memcpy(q, nq, sizeof(q));
+    }
+    memcpy(q_out, q, sizeof(q));
+    const int s0 = ttc_cell(s->si, ttc_lane(s->y[0]), 0);
+    int best = 0;
+    for (int a = 1; a < TTC_A; ++a)
+        if (q[s0][a] > q[s0][best]) best = a;
+    *state = s0;
+    *action = best;
+    return sweeps;
+}
+
+/* n scenes one after the other (the CPU data point beside b2_highway_ttc_vi) */
+void hl_ttc_value_iteration_batch(const int32_t* words, int n, double gamma, int iterations, int32_t* actions) {
+    static double q[TTC_S][TTC_A];
+    int32_t st;
+    for (int e = 0; e < n; ++e)
+        hl_ttc_value_iteration(words + (int64_t)e * HL_WORDS, gamma, iterations, 1e-5, 1e-8, &q[0][0], &st, &actions[e]);
+}

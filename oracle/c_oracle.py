@@ -28,6 +28,7 @@ def load():
         _lib.opd_highway_plan_wave.restype = ctypes.c_int
         _lib.mcts_highway_plan.restype = ctypes.c_int
         _lib.mcts_highway_plan_wave.restype = ctypes.c_int
+        _lib.hl_ttc_value_iteration.restype = ctypes.c_int
     return _lib
 
 
@@ -123,3 +124,32 @@ def mcts_plan_wave(root_words, episodes, horizon, gamma, temperature, width, see
     out = dict(i32)
     out["vsum"], out["value"], out["env_steps"] = vsum, value, steps
     return out
+
+
+def ttc_grid(words):
+    """TTC cost grid [3, 4, 10] of a scene (docs/HIGHWAY_LITE_SPEC.md section 9)."""
+    lib = load()
+    w = np.ascontiguousarray(words, dtype=np.int32)
+    g = np.zeros((3, 4, 10), dtype=np.float64)
+    lib.hl_ttc_grid(_p(w), _p(g))
+    return g
+
+
+def ttc_value_iteration(words, gamma, iterations, rtol=1e-5, atol=1e-8):
+    """ValueIterationAgent on the scene's TTC-grid MDP: (Q [120, 5], mdp.state, action, sweeps)."""
+    lib = load()
+    w = np.ascontiguousarray(words, dtype=np.int32)
+    q = np.zeros((120, 5), dtype=np.float64)
+    st, act = ctypes.c_int32(0), ctypes.c_int32(0)
+    sweeps = lib.hl_ttc_value_iteration(_p(w), ctypes.c_double(gamma), ctypes.c_int(int(iterations)), ctypes.c_double(rtol),
+                                        ctypes.c_double(atol), _p(q), ctypes.byref(st), ctypes.byref(act))
+    return q, int(st.value), int(act.value), int(sweeps)
+
+
+def ttc_value_iteration_batch(words, gamma, iterations):
+    """Actions for n scenes, one after the other on one core (the CPU data point beside b2_highway_ttc_vi)."""
+    lib = load()
+    w = np.ascontiguousarray(words, dtype=np.int32).reshape(-1, 136)
+    a = np.zeros(len(w), dtype=np.int32)
+    lib.hl_ttc_value_iteration_batch(_p(w), ctypes.c_int(len(w)), ctypes.c_double(gamma), ctypes.c_int(int(iterations)), _p(a))
+    return a

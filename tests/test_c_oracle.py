@@ -72,3 +72,23 @@ def test_c_mcts_matches_reference_golden_and_python_restatement():
     assert tc["parent"].tolist() == tp.parent and tc["count"].tolist() == tp.count and tc["action"].tolist() == tp.action
     assert np.array_equal(tc["value"], np.array(tp.value))
     assert w.tolist() == PCG64.from_numpy(rng).words().tolist()          # same stream position afterwards
+
+
+def test_c_ttc_value_iteration_matches_reference_goldens_and_numpy_oracle():
+    """Third statement of docs/HIGHWAY_LITE_SPEC.md section 9 (TTC-grid MDP + the VI agent's fixed point): against the
+    goldens of the unmodified reference agent and against the numpy oracle on the edge scenes."""
+    from tests.util import load_golden, ttc_edge_scenes
+    V = load_golden("golden_highway_vi.json")
+    for c in V["cases"]:
+        w = np.array(c["words"], dtype=np.int32)
+        assert np.array_equal(c_oracle.ttc_grid(w), np.array(c["grid"]))
+        q, st, act, _ = c_oracle.ttc_value_iteration(w, c["config"].get("gamma", 1.0), c["config"]["iterations"])
+        assert np.array_equal(q, np.array(c["q"])) and st == c["state"] and act == c["act"]
+    for w in ttc_edge_scenes():
+        mdp = oenvs.highway_finite_mdp(oenvs.HighwayLiteState.unpack(w))
+        for gamma, iterations in ((1.0, 10), (0.9, 100), (1.0, 0)):
+            q_ref, sweeps_ref = planners.value_iteration("deterministic", mdp.transition, mdp.reward, mdp.terminal, gamma,
+                                                         iterations)
+            q, st, act, sweeps = c_oracle.ttc_value_iteration(w, gamma, iterations)
+            assert np.array_equal(q, q_ref) and sweeps == sweeps_ref and st == mdp.state
+            assert act == int(np.argmax(q_ref[mdp.state]))
